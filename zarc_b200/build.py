@@ -1,0 +1,100 @@
+"""Build libzarcgpu.so (product: nvcc, sm_100a) in-tree, and -- for the CPU test-suite only -- the
+SIMT-emulator build of the very same kernel sources (tests/simt_emu/, g++)."""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "zarc_b200", "csrc")
+PRODUCT_SO = os.path.join(ROOT, "zarc_b200", "libzarcgpu.so")
+EMU_DIR = os.path.join(ROOT, "tests", "simt_emu")
+EMU_SO = os.path.join(EMU_DIR, "libzarcgpu_emu.so")
+OBJ = os.path.join(ROOT, "build")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _deps_mtime():
+    files = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    return max(os.path.getmtime(f) for f in files)
+
+
+def _stale(target: str, extra: list[str] = ()) -> bool:
+    if not os.path.exists(target):
+        return True
+    m = max([_deps_mtime()] + [os.path.getmtime(f) for f in extra])
+    return os.path.getmtime(target) < m
+
+
+def build_product(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -> zarc_b200/libzarcgpu.so.  Cross-compiles without a GPU."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not force and not _stale(PRODUCT_SO):
+        return PRODUCT_SO
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libzarcgpu.so (there is no CPU fallback)")
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    procs = []
+    for src in _sources():
+        o = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        objs.append(o)
+        cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-c", src, "-o", o]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {os.path.basename(src)}\n{out}")
+        if p.returncode:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src}")
+    with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    subprocess.check_call([nvcc, "-shared", "-o", PRODUCT_SO, *objs, "-lcudart"])
+    return PRODUCT_SO
+
+
+def build_emu(force: bool = False) -> str:
+    """g++ -DZG_EMU -> tests/simt_emu/libzarcgpu_emu.so (TEST INFRASTRUCTURE ONLY)."""
+    emu_src = [os.path.join(EMU_DIR, "simt_emu.cpp")]
+    if not force and not _stale(EMU_SO, emu_src + [os.path.join(EMU_DIR, "simt_emu.h")]):
+        return EMU_SO
+    os.makedirs(os.path.join(OBJ, "emu"), exist_ok=True)
+    objs = []
+    procs = []
+    flags = ["-O2", "-g", "-std=c++17", "-fPIC", "-DZG_EMU", "-I", EMU_DIR, "-I", CSRC, "-Wall", "-Wno-unused-function",
+             "-Wno-unknown-pragmas", "-Wno-unused-variable", "-Wno-sign-compare", "-Wno-stringop-overflow", "-Wno-maybe-uninitialized", "-Wno-array-bounds"]
+    for src in _sources() + emu_src:
+        o = os.path.join(OBJ, "emu", os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        objs.append(o)
+        cmd = ["g++", *flags, "-x", "c++", "-c", src, "-o", o]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if out.strip():
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"g++ (emu) failed on {src}")
+    subprocess.check_call(["g++", "-shared", "-o", EMU_SO, *objs])
+    return EMU_SO
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["product"]
+    if "product" in which:
+        print(build_product(force="--force" in which, verbose="-v" in which))
+    if "emu" in which:
+        print(build_emu(force="--force" in which))

@@ -1,0 +1,72 @@
+// Internal declarations shared by the kernels' launchers and the C ABI.
+#pragma once
+#include "simt.h"
+#include "../../include/zarcgpu.h"
+
+#define ZG_ERR(code) ((size_t)0 - (size_t)(code))
+
+extern uint64_t g_zg_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#define ZG_COUNT_LAUNCH() (++g_zg_launches)
+
+// grow-only device buffer
+struct ZgBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T>
+	T* as() const { return (T*)p; }
+};
+struct ZgHostBuf {  // grow-only pinned host buffer
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() {
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T>
+	T* as() const { return (T*)p; }
+};
+
+int zg_sm_count();
+
+// ---- blake3.cu ----
+struct ZgB3Work {
+	ZgBuf big;     // u64 pairs {file idx, len}
+	ZgBuf ctr;     // u32 counters
+	ZgBuf base;    // u64 group prefix per big file
+	ZgBuf nodes;   // level-5 chaining values of big files
+	ZgHostBuf h;   // pinned staging for the big list
+};
+size_t zg_blake3_run(cudaStream_t s, ZgB3Work& w, const u8* blob, const u64* off, const u64* len, u64 n, u8* digests);
+void zg_b3work_free(ZgB3Work& w);
+
+// ---- xxh64.cu ----
+size_t zg_xxh64_run(cudaStream_t s, const u8* blob, const u64* off, const u64* len, u64 n, u64* hashes);
+
+// ---- corpus.cu ----
+size_t zg_corpus_run(cudaStream_t s, u8* out, const u64* seg_off, const u32* seg_len, const u8* seg_kind, const u64* seg_key, u64 nseg);

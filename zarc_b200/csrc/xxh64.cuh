@@ -1,0 +1,90 @@
+// XXH64 device functions (seed 0 for the Zstandard Content_Checksum, RFC 8878 §3.1.1; the low
+// 32 bits are what libzstd appends when ZSTD_c_checksumFlag is set, as crates/zarc-cli/src/pack.rs:227
+// does).  Constants: SURVEY.md App. D.  The four lanes are a serial multiply-rotate chain per input.
+#pragma once
+#include "simt.h"
+
+#define XXP1 0x9E3779B185EBCA87ULL
+#define XXP2 0xC2B2AE3D27D4EB4FULL
+#define XXP3 0x165667B19E3779F9ULL
+#define XXP4 0x85EBCA77C2B2AE63ULL
+#define XXP5 0x27D4EB2F165667C5ULL
+
+ZG_DEV u64 xx_rotl(u64 x, int n) { return (x << n) | (x >> (64 - n)); }
+ZG_DEV u64 xx_round(u64 acc, u64 v) { return xx_rotl(acc + v * XXP2, 31) * XXP1; }
+ZG_DEV u64 xx_merge(u64 h, u64 v) { return (h ^ xx_round(0, v)) * XXP1 + XXP4; }
+
+struct XxState {
+	u64 v1, v2, v3, v4;
+};
+ZG_DEV void xx_init(XxState& s, u64 seed) {
+	s.v1 = seed + XXP1 + XXP2;
+	s.v2 = seed + XXP2;
+	s.v3 = seed;
+	s.v4 = seed - XXP1;
+}
+ZG_DEV void xx_stripe(XxState& s, u64 a, u64 b, u64 c, u64 d) {
+	s.v1 = xx_round(s.v1, a);
+	s.v2 = xx_round(s.v2, b);
+	s.v3 = xx_round(s.v3, c);
+	s.v4 = xx_round(s.v4, d);
+}
+// finish: `tail` points at the < 32 remaining bytes, n = total length
+ZG_DEV u64 xx_finish(const XxState& s, const u8* tail, u64 n, u64 seed) {
+	u64 h;
+	if (n >= 32) {
+		h = xx_rotl(s.v1, 1) + xx_rotl(s.v2, 7) + xx_rotl(s.v3, 12) + xx_rotl(s.v4, 18);
+		h = xx_merge(h, s.v1);
+		h = xx_merge(h, s.v2);
+		h = xx_merge(h, s.v3);
+		h = xx_merge(h, s.v4);
+	} else {
+		h = seed + XXP5;
+	}
+	h += n;
+	u32 rem = (u32)(n & 31);
+	while (rem >= 8) {
+		h = xx_rotl(h ^ xx_round(0, zg_ld64(tail)), 27) * XXP1 + XXP4;
+		tail += 8;
+		rem -= 8;
+	}
+	if (rem >= 4) {
+		h = xx_rotl(h ^ ((u64)zg_ld32(tail) * XXP1), 23) * XXP2 + XXP3;
+		tail += 4;
+		rem -= 4;
+	}
+	while (rem) {
+		h = xx_rotl(h ^ ((u64)*tail * XXP5), 11) * XXP1;
+		tail++;
+		rem--;
+	}
+	h ^= h >> 33;
+	h *= XXP2;
+	h ^= h >> 29;
+	h *= XXP3;
+	h ^= h >> 32;
+	return h;
+}
+ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
+	XxState s;
+	xx_init(s, seed);
+	u64 stripes = n >> 5;
+	if (((uintptr_t)p & 7) == 0) {
+		const ulonglong2* q = (const ulonglong2*)p;
+		if (((uintptr_t)p & 15) == 0) {
+			for (u64 i = 0; i < stripes; i++) {
+				ulonglong2 a = q[2 * i], b = q[2 * i + 1];
+				xx_stripe(s, a.x, a.y, b.x, b.y);
+			}
+		} else {
+			const u64* w = (const u64*)p;
+			for (u64 i = 0; i < stripes; i++) xx_stripe(s, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+		}
+	} else {
+		for (u64 i = 0; i < stripes; i++) {
+			const u8* b = p + 32 * i;
+			xx_stripe(s, zg_ld64(b), zg_ld64(b + 8), zg_ld64(b + 16), zg_ld64(b + 24));
+		}
+	}
+	return xx_finish(s, p + 32 * stripes, n, seed);
+}
