@@ -52,6 +52,9 @@ zg_error_code zg_get_error_code(size_t code);
 int zg_device_count(void);
 size_t zg_set_device(int device);
 const char* zg_build_info(void); /* "sm_100a" for the product build */
+/* page-locked host memory for callers that want full-rate host<->device copies (optional) */
+void* zg_alloc_pinned(size_t bytes);
+void zg_free_pinned(void* p);
 
 /* ---- parameters (libzstd's ZSTD_cParameter numbers; crates/zarc/src/encode.rs:12,84-89;
  *      CLI mapping crates/zarc-cli/src/pack.rs:89-114,140-195,227-237) ---------------------- */

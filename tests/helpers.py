@@ -34,3 +34,43 @@ def xxh64_batch(lib, files, align=1, shift=0):
     out = np.zeros(len(files), dtype=np.uint64)
     lib.check(lib.zg_xxh64_batch(blob.ctypes.data, off.ctypes.data, lens.ctypes.data, len(files), out.ctypes.data))
     return [int(v) for v in out]
+
+
+def unpack_batch(lib, frames, ulens, digests=None, dctx=None, verify_checksum=True, junk_prefix=7):
+    """Concatenate frames (with a junk prefix so offsets are non-trivial) and run zg_unpack_batch.
+    Returns (outputs list[bytes], ok list[int] | None, status list[int], rc)."""
+    archive = bytearray(b"\xAA" * junk_prefix)
+    offs, lens = [], []
+    for f in frames:
+        offs.append(len(archive))
+        lens.append(len(f))
+        archive += f
+    n = len(frames)
+    arch = np.frombuffer(bytes(archive) or b"\0", dtype=np.uint8).copy()
+    off = np.array(offs, dtype=np.uint64)
+    ln = np.array(lens, dtype=np.uint64)
+    ul = np.array(ulens, dtype=np.uint64)
+    total = int(ul.sum())
+    out = np.zeros(max(total, 1), dtype=np.uint8)
+    ok = np.zeros(max(n, 1), dtype=np.uint8)
+    status = np.zeros(max(n, 1), dtype=np.uint32)
+    dig = None
+    if digests is not None:
+        dig = np.frombuffer(b"".join(digests) or b"\0" * 32, dtype=np.uint8).copy()
+    own = dctx is None
+    if own:
+        dctx = lib.zg_dctx_create()
+        assert dctx, "zg_dctx_create failed"
+    try:
+        lib.zg_dctx_set_verify_checksum(dctx, 1 if verify_checksum else 0)
+        rc = lib.zg_unpack_batch(dctx, arch.ctypes.data, len(archive), n, off.ctypes.data, ln.ctypes.data, ul.ctypes.data,
+                                 dig.ctypes.data if dig is not None else None, out.ctypes.data, total, None,
+                                 ok.ctypes.data if dig is not None else None, status.ctypes.data)
+    finally:
+        if own:
+            lib.zg_dctx_free(dctx)
+    outs, pos = [], 0
+    for u in ulens:
+        outs.append(bytes(out[pos : pos + u]))
+        pos += u
+    return outs, (list(map(int, ok[:n])) if dig is not None else None), list(map(int, status[:n])), rc

@@ -1,0 +1,125 @@
+"""Per-kernel device-resident micro-benchmarks (CUDA events on the launching stream)."""
+import argparse
+import json
+import sys
+import os
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from zarc_b200 import lib as product_lib, corpus  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(a).cuda()
+
+
+def gen_corpus(lib, c, stream=0):
+    so, sl, sk, key = c.segments()
+    blob = torch.empty(max(c.blob_bytes, 1) + 64, dtype=torch.uint8, device="cuda")
+    d = [dev(x) for x in (so, sl, sk, key)]
+    lib.check(lib.zg_corpus_generate_dev(stream, blob.data_ptr(), d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), len(so)))
+    torch.cuda.synchronize()
+    return blob
+
+
+def timeit(fn, iters=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gb", type=float, default=2.0)
+    ap.add_argument("--what", default="blake3,xxh64")
+    ap.add_argument("--sample-mb", type=float, default=100)
+    ap.add_argument("--replicas", type=int, default=10)
+    ap.add_argument("--level", type=int, default=3)
+    args = ap.parse_args()
+    lib = product_lib()
+    res = {}
+    c = corpus.c2_source_tree(total_bytes=int(args.gb * 1e9))
+    t0 = time.time()
+    blob = gen_corpus(lib, c)
+    res["gen_s"] = time.time() - t0
+    off, ln = dev(c.off), dev(c.len)
+    n = c.n_files
+    s = torch.cuda.current_stream().cuda_stream
+    if "blake3" in args.what:
+        dig = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        best, med = timeit(lambda: lib.check(lib.zg_blake3_batch_dev(s, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, dig.data_ptr())))
+        res["blake3_c2_gbs"] = c.total_bytes / best / 1e6
+        c3 = corpus.c3_huge(n_files=4, file_bytes=512 << 20)
+        b3 = gen_corpus(lib, c3)
+        o3, l3 = dev(c3.off), dev(c3.len)
+        d3 = torch.empty(4 * 32, dtype=torch.uint8, device="cuda")
+        best, med = timeit(lambda: lib.check(lib.zg_blake3_batch_dev(s, b3.data_ptr(), o3.data_ptr(), l3.data_ptr(), 4, d3.data_ptr())))
+        res["blake3_c3_gbs"] = c3.total_bytes / best / 1e6
+        del b3
+    if "xxh64" in args.what:
+        h = torch.empty(n, dtype=torch.int64, device="cuda")
+        best, med = timeit(lambda: lib.check(lib.zg_xxh64_batch_dev(s, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, h.data_ptr())))
+        res["xxh64_c2_gbs"] = c.total_bytes / best / 1e6
+    if "decode" in args.what:
+        from oracle import ref_path
+        import concurrent.futures as cf
+
+        cs = corpus.c2_source_tree(total_bytes=int(args.sample_mb * 1e6), seed=5)
+        hblob = corpus.materialise_host(lib, cs)
+        datas = [bytes(hblob[int(o) : int(o) + int(l)]) for o, l in zip(cs.off, cs.len)]
+        t0 = time.time()
+        frames = [ref_path.ref_compress(d, level=args.level) for d in datas]
+        res["ref_compress_gbs_1core"] = cs.total_bytes / (time.time() - t0) / 1e9
+        res["ref_ratio"] = cs.total_bytes / sum(len(f) for f in frames)
+        arch = np.frombuffer(b"".join(frames), dtype=np.uint8)
+        flen = np.array([len(f) for f in frames], dtype=np.uint64)
+        foff = (np.cumsum(flen) - flen).astype(np.uint64)
+        R = args.replicas
+        A = len(arch)
+        d_arch = dev(arch).repeat(R)
+        off_r = np.concatenate([foff + np.uint64(r * A) for r in range(R)])
+        len_r = np.tile(flen, R)
+        ul_r = np.tile(cs.len, R)
+        oo_r = (np.cumsum(ul_r) - ul_r).astype(np.uint64)
+        total = int(ul_r.sum())
+        d_out = torch.empty(total + 64, dtype=torch.uint8, device="cuda")
+        d_off, d_len, d_ul, d_oo = dev(off_r), dev(len_r), dev(ul_r), dev(oo_r)
+        K = len(off_r)
+        d_status = torch.zeros(K, dtype=torch.int32, device="cuda")
+        dctx = lib.zg_dctx_create()
+        lib.zg_dctx_set_stream(dctx, s)
+        for vc in (0, 1):
+            lib.zg_dctx_set_verify_checksum(dctx, vc)
+            best, med = timeit(lambda: lib.check(lib.zg_unpack_batch_dev(dctx, d_arch.data_ptr(), A * R, K, d_off.data_ptr(), d_len.data_ptr(),
+                               d_ul.data_ptr(), None, d_out.data_ptr(), total, d_oo.data_ptr(), None, d_status.data_ptr())), iters=3, warmup=1)
+            res[f"decode_c2_L{args.level}_gbs_ck{vc}"] = total / best / 1e6
+        # check the bytes of replica 0 and the last replica
+        ho = d_out[: cs.total_bytes].cpu().numpy().tobytes()
+        res["decode_ok"] = ho == b"".join(datas) and int(d_status.abs().sum()) == 0
+        res["decode_total_gb"] = total / 1e9
+        # + BLAKE3 verify
+        dig = np.frombuffer(b"".join(__import__("blake3").blake3(d).digest() for d in datas), dtype=np.uint8)
+        d_dig = dev(np.tile(dig, R))
+        d_ok = torch.zeros(K, dtype=torch.uint8, device="cuda")
+        best, med = timeit(lambda: lib.check(lib.zg_unpack_batch_dev(dctx, d_arch.data_ptr(), A * R, K, d_off.data_ptr(), d_len.data_ptr(),
+                           d_ul.data_ptr(), d_dig.data_ptr(), d_out.data_ptr(), total, d_oo.data_ptr(), d_ok.data_ptr(), d_status.data_ptr())), iters=3, warmup=1)
+        res[f"unpack_verify_c2_L{args.level}_gbs"] = total / best / 1e6
+        res["verify_all_ok"] = int(d_ok.sum()) == K
+        lib.zg_dctx_free(dctx)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,6 @@
 // C ABI of libzarcgpu (include/zarcgpu.h): contexts, host<->device staging, error names.
 // Everything that touches content bytes is a CUDA kernel; the host code here only moves buffers
-// and does bookkeeping on sizes/offsets.
+// and does bookkeeping on sizes/offsets (frame/block *header* walks to find frame boundaries).
 #include "common.h"
 #include <new>
 #include <vector>
@@ -33,6 +33,107 @@ int zg_sm_count() {
 	do {                 \
 		if (dev_count() <= 0) return ZG_ERR(ZG_error_no_device); \
 	} while (0)
+#define ZG_TRY(expr)              \
+	do {                          \
+		size_t r_ = (expr);       \
+		if (zg_is_error(r_)) return r_; \
+	} while (0)
+#define ZG_CUDA(expr) \
+	do {              \
+		if ((expr) != cudaSuccess) return ZG_ERR(ZG_error_device); \
+	} while (0)
+#define ZG_ALLOC(expr) \
+	do {               \
+		if ((expr) != cudaSuccess) return ZG_ERR(ZG_error_memory_allocation); \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------
+// host-side frame boundary walk: frame header + 3-byte block headers only (no content decoding).
+// Returns 0 if more input is needed, an error, or the frame's total length.  *bound = upper bound
+// on the decoded size (FCS when present, else 128 KiB per block).
+static size_t host_frame_size(const uint8_t* p, size_t n, uint64_t* bound, bool* has_fcs = nullptr) {
+	if (n < 5) return 0;
+	uint32_t magic = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+	if (magic != 0xFD2FB528u) return ZG_ERR(ZG_error_prefix_unknown);
+	uint32_t desc = p[4];
+	uint32_t fcs_flag = desc >> 6, single = (desc >> 5) & 1, checksum = (desc >> 2) & 1, did_flag = desc & 3;
+	if (desc & 8) return ZG_ERR(ZG_error_frameParameter_unsupported);
+	size_t ip = 5 + (single ? 0 : 1) + (did_flag == 3 ? 4 : did_flag);
+	uint32_t fcs_len = fcs_flag == 0 ? single : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+	if (n < ip + fcs_len) return 0;
+	uint64_t fcs = 0;
+	for (uint32_t i = 0; i < fcs_len; i++) fcs |= (uint64_t)p[ip + i] << (8 * i);
+	if (fcs_len == 2) fcs += 256;
+	ip += fcs_len;
+	uint64_t blocks = 0;
+	for (;;) {
+		if (n < ip + 3) return 0;
+		uint32_t bh = (uint32_t)p[ip] | ((uint32_t)p[ip + 1] << 8) | ((uint32_t)p[ip + 2] << 16);
+		uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+		if (type == 3) return ZG_ERR(ZG_error_corruption_detected);
+		ip += 3 + (type == 1 ? 1 : bsize);
+		blocks++;
+		if (last) break;
+	}
+	if (checksum) ip += 4;
+	if (n < ip) return 0;
+	if (bound) *bound = fcs_len ? fcs : blocks * 131072ull;
+	if (has_fcs) *has_fcs = fcs_len != 0;
+	return ip;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct zg_dctx {
+	cudaStream_t stream = 0;
+	bool own_stream = false;
+	int verify_checksum = 1;
+	ZgZdWork zd;
+	ZgB3Work b3;
+	ZgBuf status, produced, cksums, got_digests, first, tiles, packed_off;
+	// host-API staging
+	ZgBuf d_archive, d_meta, d_out, d_digests, d_ok;
+	ZgHostBuf h_first, h_small;
+	// streaming state (zg_decompress_stream)
+	std::vector<uint8_t> in_acc, out_acc;
+	size_t out_pos = 0;
+	int stage = 0;  // 0 collecting input, 1 flushing output
+};
+
+// device-pointer core of unpack: decode, verify sizes/checksums, optional BLAKE3 verify, first error
+static size_t unpack_core(zg_dctx* d, const u8* archive, u64 archive_len, u64 n, const u64* off, const u64* len, const u64* ulen,
+                          const u8* digests, u8* out, u64 out_cap, const u64* out_off, u8* ok, u32* status) {
+	cudaStream_t s = d->stream;
+	if (n == 0) return 0;
+	ZG_ALLOC(d->produced.reserve(n * 8));
+	ZG_ALLOC(d->cksums.reserve(n * 8));
+	ZG_ALLOC(d->first.reserve(8));
+	ZG_ALLOC(d->h_first.reserve(8));
+	u32* st = status;
+	if (!st) {
+		ZG_ALLOC(d->status.reserve(n * 4));
+		st = d->status.as<u32>();
+	}
+	if (!out_off) {
+		ZG_ALLOC(d->packed_off.reserve(n * 8));
+		ZG_TRY(zg_scan_run(s, d->tiles, ulen, n, 0, d->packed_off.as<u64>(), nullptr));
+		out_off = d->packed_off.as<u64>();
+	}
+	ZG_TRY(zg_zstd_decode_run(s, d->zd, archive, archive_len, off, len, ulen, out_off, n, out, out_cap, st, d->produced.as<u64>(),
+	                          d->cksums.as<u32>()));
+	ZG_TRY(zg_unpack_finalize_run(s, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum));
+	if (digests && ok) {
+		ZG_ALLOC(d->got_digests.reserve(n * 32));
+		ZG_TRY(zg_blake3_run(s, d->b3, out, out_off, ulen, n, d->got_digests.as<u8>()));
+		ZG_TRY(zg_digest_compare_run(s, d->got_digests.as<u8>(), digests, st, ok, n));
+	}
+	ZG_TRY(zg_first_error_run(s, st, n, d->first.as<u64>()));
+	u64* hf = d->h_first.as<u64>();
+	ZG_CUDA(cudaMemcpyAsync(hf, d->first.p, 8, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	ZG_CUDA(cudaGetLastError());
+	if (*hf != ~0ull) return ZG_ERR((size_t)(*hf & 0xff));
+	return 0;
+}
 
 extern "C" {
 
@@ -75,6 +176,14 @@ const char* zg_build_info(void) {
 #endif
 }
 uint64_t zg_kernel_launch_count(void) { return g_zg_launches; }
+void* zg_alloc_pinned(size_t n) {
+	void* p = nullptr;
+	if (dev_count() <= 0 || cudaMallocHost(&p, n ? n : 1) != cudaSuccess) return nullptr;
+	return p;
+}
+void zg_free_pinned(void* p) {
+	if (p) cudaFreeHost(p);
+}
 
 // ---------------------------------------------------------------------------------------------
 // building blocks, device pointers
@@ -94,6 +203,14 @@ size_t zg_corpus_generate_dev(void* stream, uint8_t* out, const uint64_t* seg_of
                               const uint8_t* seg_kind, const uint64_t* seg_key, uint64_t n) {
 	ZG_NEED_DEVICE();
 	return zg_corpus_run((cudaStream_t)stream, out, seg_off, seg_len, seg_kind, seg_key, n);
+}
+size_t zg_assign_offsets_dev(void* stream, const uint64_t* frame_len, uint64_t n, uint64_t base, uint64_t* frame_off) {
+	ZG_NEED_DEVICE();
+	ZgBuf tiles;
+	size_t r = zg_scan_run((cudaStream_t)stream, tiles, frame_len, n, base, frame_off, nullptr);
+	cudaStreamSynchronize((cudaStream_t)stream);
+	tiles.release();
+	return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -153,4 +270,268 @@ size_t zg_xxh64_batch(const uint8_t* blob, const uint64_t* off, const uint64_t* 
 	return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// streaming Hasher: blake3::Hasher::{new,update,finalize} (decode/frame_iterator.rs:54,99,77).
+// update() buffers; finalize() hashes the buffered bytes on the GPU (the digest of a stream is
+// only observable at finalize, so this is semantically identical).
+struct zg_hasher {
+	std::vector<uint8_t> acc;
+};
+zg_hasher* zg_hasher_new(void) { return new (std::nothrow) zg_hasher(); }
+size_t zg_hasher_update(zg_hasher* h, const void* data, size_t len) {
+	if (!h) return ZG_ERR(ZG_error_GENERIC);
+	const uint8_t* p = (const uint8_t*)data;
+	h->acc.insert(h->acc.end(), p, p + len);
+	return 0;
+}
+size_t zg_hasher_finalize(zg_hasher* h, uint8_t out[32]) {
+	if (!h) return ZG_ERR(ZG_error_GENERIC);
+	return zg_blake3(h->acc.data(), h->acc.size(), out);
+}
+void zg_hasher_free(zg_hasher* h) { delete h; }
+
+// ---------------------------------------------------------------------------------------------
+// decompression context
+zg_dctx* zg_dctx_create(void) {
+	if (dev_count() <= 0) return nullptr;
+	zg_dctx* d = new (std::nothrow) zg_dctx();
+	if (!d) return nullptr;
+	if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		delete d;
+		return nullptr;
+	}
+	d->own_stream = true;
+	return d;
+}
+void zg_dctx_free(zg_dctx* d) {
+	if (!d) return;
+	cudaStreamSynchronize(d->stream);
+	d->zd.lit.release();
+	d->zd.queue.release();
+	zg_b3work_free(d->b3);
+	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->d_archive,
+	                 &d->d_meta, &d->d_out, &d->d_digests, &d->d_ok})
+		b->release();
+	d->h_first.release();
+	d->h_small.release();
+	if (d->own_stream) cudaStreamDestroy(d->stream);
+	delete d;
+}
+size_t zg_dctx_set_stream(zg_dctx* d, void* stream) {
+	if (!d) return ZG_ERR(ZG_error_GENERIC);
+	if (d->own_stream) cudaStreamDestroy(d->stream);
+	d->own_stream = false;
+	d->stream = (cudaStream_t)stream;
+	return 0;
+}
+size_t zg_dctx_set_verify_checksum(zg_dctx* d, int on) {
+	if (!d) return ZG_ERR(ZG_error_GENERIC);
+	d->verify_checksum = on ? 1 : 0;
+	return 0;
+}
+size_t zg_dstream_in_size(void) { return 131075; }   // ZSTD_DStreamInSize: block max + block header
+size_t zg_dstream_out_size(void) { return 131072; }  // ZSTD_DStreamOutSize
+size_t zg_find_frame_compressed_size(const void* src, size_t n) {
+	size_t r = host_frame_size((const uint8_t*)src, n, nullptr);
+	return r == 0 ? ZG_ERR(ZG_error_srcSize_wrong) : r;
+}
+
+size_t zg_unpack_batch_dev(zg_dctx* d, const uint8_t* archive, uint64_t archive_len, uint64_t n, const uint64_t* off,
+                           const uint64_t* len, const uint64_t* ulen, const uint8_t* digests, uint8_t* out, uint64_t out_cap,
+                           const uint64_t* out_off, uint8_t* ok, uint32_t* status) {
+	ZG_NEED_DEVICE();
+	if (!d) return ZG_ERR(ZG_error_GENERIC);
+	if (!out && n) return ZG_ERR(ZG_error_dstBuffer_null);
+	return unpack_core(d, archive, archive_len, n, off, len, ulen, digests, out, out_cap, out_off, ok, status);
+}
+
+size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len, uint64_t n, const uint64_t* off,
+                       const uint64_t* len, const uint64_t* ulen, const uint8_t* digests, uint8_t* out, uint64_t out_cap,
+                       const uint64_t* out_off, uint8_t* ok, uint32_t* status) {
+	ZG_NEED_DEVICE();
+	if (!d) return ZG_ERR(ZG_error_GENERIC);
+	if (n == 0) return 0;
+	if (!out) return ZG_ERR(ZG_error_dstBuffer_null);
+	cudaStream_t s = d->stream;
+	// bookkeeping on offsets: the archive span this batch touches, and the output layout
+	u64 lo = ~0ull, hi = 0, total = 0;
+	bool dense = true;
+	for (u64 k = 0; k < n; k++) {
+		if (off[k] > archive_len || len[k] > archive_len - off[k]) return ZG_ERR(ZG_error_srcSize_wrong);
+		lo = off[k] < lo ? off[k] : lo;
+		hi = off[k] + len[k] > hi ? off[k] + len[k] : hi;
+		if (out_off && out_off[k] != total) dense = false;
+		total += ulen[k];
+	}
+	u64 out_lo = 0, out_hi = total;
+	if (out_off && !dense) {
+		out_lo = ~0ull;
+		out_hi = 0;
+		for (u64 k = 0; k < n; k++) {
+			if (out_off[k] > out_cap || ulen[k] > out_cap - out_off[k]) return ZG_ERR(ZG_error_dstSize_tooSmall);
+			out_lo = out_off[k] < out_lo ? out_off[k] : out_lo;
+			out_hi = out_off[k] + ulen[k] > out_hi ? out_off[k] + ulen[k] : out_hi;
+		}
+	} else if (total > out_cap) {
+		return ZG_ERR(ZG_error_dstSize_tooSmall);
+	}
+	u64 span = hi - lo, ospan = out_hi - out_lo;
+	// device arrays: off' (rebased), len, ulen, out_off' (rebased)
+	ZG_ALLOC(d->d_archive.reserve(span + 16));
+	ZG_ALLOC(d->d_meta.reserve(n * 32));
+	ZG_ALLOC(d->d_out.reserve(ospan + 16));
+	ZG_ALLOC(d->d_ok.reserve(n * 5));
+	ZG_ALLOC(d->h_small.reserve(n * 16));
+	u64* h_off = d->h_small.as<u64>();
+	u64* h_oo = h_off + n;
+	u64 acc = 0;
+	for (u64 k = 0; k < n; k++) {
+		h_off[k] = off[k] - lo;
+		h_oo[k] = (out_off && !dense) ? out_off[k] - out_lo : acc;
+		acc += ulen[k];
+	}
+	u64* m = d->d_meta.as<u64>();
+	ZG_CUDA(cudaMemcpyAsync(d->d_archive.p, archive + lo, span, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m, h_off, n * 8, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m + n, len, n * 8, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m + 2 * n, ulen, n * 8, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m + 3 * n, h_oo, n * 8, cudaMemcpyHostToDevice, s));
+	u8* d_dig = nullptr;
+	if (digests && ok) {
+		ZG_ALLOC(d->d_digests.reserve(n * 32));
+		d_dig = d->d_digests.as<u8>();
+		ZG_CUDA(cudaMemcpyAsync(d_dig, digests, n * 32, cudaMemcpyHostToDevice, s));
+	}
+	u8* d_okp = d->d_ok.as<u8>();
+	u32* d_status = (u32*)(d_okp + ((n + 3) & ~(u64)3));
+	size_t r = unpack_core(d, d->d_archive.as<u8>(), span, n, m, m + n, m + 2 * n, d_dig, d->d_out.as<u8>(), ospan, m + 3 * n,
+	                       d_dig ? d_okp : nullptr, d_status);
+	if (zg_is_error(r) && (zg_get_error_code(r) == ZG_error_device || zg_get_error_code(r) == ZG_error_memory_allocation)) return r;
+	if (out_off && !dense) {
+		std::vector<u8> tmp(ospan);
+		ZG_CUDA(cudaMemcpyAsync(tmp.data(), d->d_out.p, ospan, cudaMemcpyDeviceToHost, s));
+		ZG_CUDA(cudaStreamSynchronize(s));
+		for (u64 k = 0; k < n; k++) memcpy(out + out_off[k], tmp.data() + (out_off[k] - out_lo), ulen[k]);
+	} else {
+		ZG_CUDA(cudaMemcpyAsync(out, d->d_out.p, total, cudaMemcpyDeviceToHost, s));
+	}
+	if (d_dig) ZG_CUDA(cudaMemcpyAsync(ok, d_okp, n, cudaMemcpyDeviceToHost, s));
+	if (status) ZG_CUDA(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	return r;
+}
+
+size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t n) {
+	ZG_NEED_DEVICE();
+	if (!d) return ZG_ERR(ZG_error_GENERIC);
+	uint64_t bound = 0;
+	bool has_fcs = false;
+	size_t fsz = host_frame_size((const uint8_t*)src, n, &bound, &has_fcs);
+	if (fsz == 0) return ZG_ERR(ZG_error_srcSize_wrong);
+	if (zg_is_error(fsz)) return fsz;
+	if (has_fcs && bound > cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
+	cudaStream_t s = d->stream;
+	u64 ocap = bound;
+	ZG_ALLOC(d->d_archive.reserve(fsz + 16));
+	ZG_ALLOC(d->d_out.reserve(ocap + 16));
+	ZG_ALLOC(d->d_meta.reserve(64));
+	ZG_ALLOC(d->produced.reserve(8));
+	ZG_ALLOC(d->cksums.reserve(8));
+	ZG_ALLOC(d->status.reserve(4));
+	ZG_ALLOC(d->h_small.reserve(64));
+	u64* hm = d->h_small.as<u64>();
+	hm[0] = 0;
+	hm[1] = fsz;
+	hm[2] = ocap;
+	hm[3] = 0;
+	u64* m = d->d_meta.as<u64>();
+	ZG_CUDA(cudaMemcpyAsync(d->d_archive.p, src, fsz, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m, hm, 32, cudaMemcpyHostToDevice, s));
+	ZG_TRY(zg_zstd_decode_run(s, d->zd, d->d_archive.as<u8>(), fsz, m, m + 1, m + 2, m + 3, 1, d->d_out.as<u8>(), ocap,
+	                          d->status.as<u32>(), d->produced.as<u64>(), d->cksums.as<u32>()));
+	// size is whatever the frame produced (FCS is checked inside the kernel when present)
+	ZG_CUDA(cudaMemcpyAsync(hm + 4, d->produced.p, 8, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	u64 produced = hm[4];
+	hm[2] = produced;
+	ZG_CUDA(cudaMemcpyAsync(m + 2, hm + 2, 8, cudaMemcpyHostToDevice, s));
+	ZG_TRY(zg_unpack_finalize_run(s, d->d_out.as<u8>(), m + 3, m + 2, d->produced.as<u64>(), d->cksums.as<u32>(), d->status.as<u32>(), 1,
+	                              d->verify_checksum));
+	u32* hst = (u32*)(hm + 5);
+	ZG_CUDA(cudaMemcpyAsync(hst, d->status.p, 4, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	if (*hst) return ZG_ERR((size_t)*hst);
+	if (produced > cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
+	if (produced) ZG_CUDA(cudaMemcpy(dst, d->d_out.p, produced, cudaMemcpyDeviceToHost));
+	return produced;
+}
+
+// DCtx::decompress_stream contract (decode/zstd_iterator.rs:104-107,126-129): consume input until the
+// frame is complete, decode it on the GPU, then hand the output out as space allows.  Returns 0
+// when the frame is fully decoded and flushed, otherwise a non-zero hint.
+size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* input) {
+	ZG_NEED_DEVICE();
+	if (!d || !output || !input) return ZG_ERR(ZG_error_GENERIC);
+	if (input->pos > input->size || output->pos > output->size) return ZG_ERR(ZG_error_srcSize_wrong);
+	if (d->stage == 0) {
+		const uint8_t* src = (const uint8_t*)input->src + input->pos;
+		size_t avail = input->size - input->pos;
+		size_t before = d->in_acc.size();
+		d->in_acc.insert(d->in_acc.end(), src, src + avail);
+		uint64_t bound = 0;
+		size_t fsz = host_frame_size(d->in_acc.data(), d->in_acc.size(), &bound);
+		if (zg_is_error(fsz)) {
+			d->in_acc.clear();
+			return fsz;
+		}
+		if (fsz == 0) {  // frame incomplete: everything offered belongs to it
+			input->pos = input->size;
+			return 3;  // at least one more block header
+		}
+		input->pos += fsz - before;  // never consume past the end of this frame
+		d->in_acc.resize(fsz);
+		d->out_acc.assign(bound ? bound : 1, 0);
+		size_t r = zg_decompress(d, d->out_acc.data(), bound, d->in_acc.data(), fsz);
+		d->in_acc.clear();
+		if (zg_is_error(r)) {
+			d->out_acc.clear();
+			return r;
+		}
+		d->out_acc.resize(r);
+		d->out_pos = 0;
+		d->stage = 1;
+	}
+	size_t room = output->size - output->pos;
+	size_t left = d->out_acc.size() - d->out_pos;
+	size_t take = room < left ? room : left;
+	if (take) memcpy((uint8_t*)output->dst + output->pos, d->out_acc.data() + d->out_pos, take);
+	output->pos += take;
+	d->out_pos += take;
+	if (d->out_pos == d->out_acc.size()) {
+		d->out_acc.clear();
+		d->out_pos = 0;
+		d->stage = 0;
+		return 0;
+	}
+	return d->out_acc.size() - d->out_pos;
+}
+
 }  // extern "C"
+
+// ---- entry points still to be wired (return GENERIC until their kernels land) -----------------
+#ifndef ZG_HAVE_ENCODER
+extern "C" {
+zg_cctx* zg_cctx_create(void) { return nullptr; }
+void zg_cctx_free(zg_cctx*) {}
+size_t zg_cctx_init(zg_cctx*, int) { return ZG_ERR(ZG_error_GENERIC); }
+size_t zg_cctx_set_parameter(zg_cctx*, int, int) { return ZG_ERR(ZG_error_GENERIC); }
+size_t zg_cctx_reset(zg_cctx*, int) { return ZG_ERR(ZG_error_GENERIC); }
+size_t zg_cctx_set_stream(zg_cctx*, void*) { return ZG_ERR(ZG_error_GENERIC); }
+size_t zg_compress2(zg_cctx*, void*, size_t, const void*, size_t) { return ZG_ERR(ZG_error_GENERIC); }
+size_t zg_compress_bound(size_t n) { return n + (n >> 8) + 64; }
+size_t zg_cctx_reset_archive(zg_cctx*, uint64_t) { return ZG_ERR(ZG_error_GENERIC); }
+uint64_t zg_cctx_archive_offset(const zg_cctx*) { return 0; }
+size_t zg_pack_batch(zg_cctx*, const uint8_t*, const uint64_t*, const uint64_t*, uint64_t, uint8_t*, uint8_t*, uint64_t*, uint64_t*, uint8_t*, uint64_t, uint64_t*) { return ZG_ERR(ZG_error_GENERIC); }
+size_t zg_pack_batch_dev(zg_cctx*, const uint8_t*, const uint64_t*, const uint64_t*, uint64_t, uint8_t*, uint8_t*, uint64_t*, uint64_t*, uint8_t*, uint64_t, uint64_t*) { return ZG_ERR(ZG_error_GENERIC); }
+}
+#endif

@@ -70,3 +70,21 @@ size_t zg_xxh64_run(cudaStream_t s, const u8* blob, const u64* off, const u64* l
 
 // ---- corpus.cu ----
 size_t zg_corpus_run(cudaStream_t s, u8* out, const u64* seg_off, const u32* seg_len, const u8* seg_kind, const u64* seg_key, u64 nseg);
+
+// ---- scan.cu ----
+size_t zg_scan_run(cudaStream_t s, ZgBuf& tiles, const u64* in, u64 n, u64 base, u64* out, u64* total_out);
+
+// ---- zstd_decode.cu ----
+struct ZgZdWork {
+	ZgBuf lit;    // per-warp literal staging
+	ZgBuf queue;  // frame queue counter
+};
+size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
+                          const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,
+                          u32* cksums);
+
+// ---- glue.cu ----
+size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off, const u64* ulen, const u64* produced,
+                              const u32* cksums, u32* status, u64 n, int verify);
+size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n);
+size_t zg_first_error_run(cudaStream_t s, const u32* status, u64 n, u64* first);

@@ -1,0 +1,59 @@
+// Small per-frame bookkeeping kernels around the codec kernels (unpack side).
+#include "common.h"
+#include "xxh64.cuh"
+#include "zstd_common.cuh"
+
+// after decode: size check against Frame.uncompressed, optional Content_Checksum verification
+// (libzstd verifies it by default; the reference never disables it, decode/zstd_iterator.rs:29)
+__global__ void __launch_bounds__(128)
+k_unpack_finalize(const u8* __restrict__ out, const u64* __restrict__ out_off, const u64* __restrict__ ulen,
+                  const u64* __restrict__ produced, const u32* __restrict__ cksums, u32* __restrict__ status, u64 n, int verify) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	u32 st = status[k];
+	if (st == ZS_OK && produced[k] != ulen[k]) st = ZS_E_CORRUPT;
+	if (st == ZS_OK && verify && cksums[2 * k + 1]) {
+		u64 h = xx_hash(out + out_off[k], ulen[k], 0);
+		if ((u32)h != cksums[2 * k]) st = ZS_E_CHECKSUM;
+	}
+	status[k] = st;
+}
+
+// ok[k] = frame decoded and BLAKE3(out_k) == expected  (FrameIterator::verify, frame_iterator.rs:86-88)
+__global__ void __launch_bounds__(128)
+k_digest_compare(const u8* __restrict__ got, const u8* __restrict__ want, const u32* __restrict__ status, u8* __restrict__ ok, u64 n) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	u32 diff = 0;
+	for (u32 i = 0; i < 32; i++) diff |= (u32)(got[32 * k + i] ^ want[32 * k + i]);  // constant time, integrity.rs:17-22
+	ok[k] = (status[k] == ZS_OK && diff == 0) ? 1 : 0;
+}
+
+// first[0] = min over failing k of (k << 8 | code); ~0 when all succeeded
+__global__ void __launch_bounds__(128) k_first_error(const u32* __restrict__ status, u64 n, unsigned long long* first) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	u32 st = status[k];
+	if (st) atomicMin(first, (unsigned long long)((k << 8) | (st & 0xff)));
+}
+
+size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off, const u64* ulen, const u64* produced,
+                              const u32* cksums, u32* status, u64 n, int verify) {
+	if (!n) return 0;
+	ZG_LAUNCH(k_unpack_finalize, (u32)((n + 127) / 128), 128, 0, s, out, out_off, ulen, produced, cksums, status, n, verify);
+	ZG_COUNT_LAUNCH();
+	return 0;
+}
+size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n) {
+	if (!n) return 0;
+	ZG_LAUNCH(k_digest_compare, (u32)((n + 127) / 128), 128, 0, s, got, want, status, ok, n);
+	ZG_COUNT_LAUNCH();
+	return 0;
+}
+size_t zg_first_error_run(cudaStream_t s, const u32* status, u64 n, u64* first) {
+	cudaMemsetAsync(first, 0xff, 8, s);
+	if (!n) return 0;
+	ZG_LAUNCH(k_first_error, (u32)((n + 127) / 128), 128, 0, s, status, n, (unsigned long long*)first);
+	ZG_COUNT_LAUNCH();
+	return 0;
+}

@@ -20,7 +20,7 @@ static inline void zg_emu_launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t s
 #define ZG_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; type* name = (type*)name##_raw_
 #define ZG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ZG_UNROLL _Pragma("unroll")
-#define ZG_CONST_TABLE __device__ const
+#define ZG_CONST_TABLE static __device__ const
 #endif
 
 #define ZG_DEV __device__ __forceinline__
@@ -31,6 +31,7 @@ typedef uint8_t u8;
 typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
+typedef int16_t i16;
 typedef int32_t i32;
 typedef int64_t i64;
 
