@@ -74,3 +74,46 @@ def unpack_batch(lib, frames, ulens, digests=None, dctx=None, verify_checksum=Tr
         outs.append(bytes(out[pos : pos + u]))
         pos += u
     return outs, (list(map(int, ok[:n])) if dig is not None else None), list(map(int, status[:n])), rc
+
+
+def compress2(lib, data, level=3, checksum=True, cctx=None, content_size=True):
+    """zg_compress2 with the reference's capacity rule (lowlevel_frames.rs:21)."""
+    import ctypes as C
+
+    own = cctx is None
+    if own:
+        cctx = lib.zg_cctx_create()
+        assert cctx
+        lib.check(lib.zg_cctx_init(cctx, 0))
+        lib.check(lib.zg_cctx_set_parameter(cctx, 201, 1 if checksum else 0))
+        lib.check(lib.zg_cctx_set_parameter(cctx, 100, level))
+        if not content_size:
+            lib.check(lib.zg_cctx_set_parameter(cctx, 200, 0))
+    try:
+        n = len(data)
+        cap = n + max(1024, n // 10)
+        dst = C.create_string_buffer(cap)
+        r = lib.check(lib.zg_compress2(cctx, dst, cap, bytes(data), n))
+        return dst.raw[:r]
+    finally:
+        if own:
+            lib.zg_cctx_free(cctx)
+
+
+def pack_batch(lib, cctx, files, align=1, cap=None):
+    """zg_pack_batch over a list of byte strings. Returns dict of numpy outputs + the new frames bytes."""
+    blob, off, lens = layout(files, align)
+    n = len(files)
+    total = int(lens.sum())
+    if cap is None:
+        cap = total + max(1024, total // 10) + 32 * n
+    digests = np.zeros((max(n, 1), 32), dtype=np.uint8)
+    first = np.zeros(max(n, 1), dtype=np.uint8)
+    foff = np.zeros(max(n, 1), dtype=np.uint64)
+    flen = np.zeros(max(n, 1), dtype=np.uint64)
+    frames = np.zeros(max(cap, 1), dtype=np.uint8)
+    nbytes = np.zeros(1, dtype=np.uint64)
+    rc = lib.zg_pack_batch(cctx, blob.ctypes.data, off.ctypes.data, lens.ctypes.data, n, digests.ctypes.data, first.ctypes.data,
+                           foff.ctypes.data, flen.ctypes.data, frames.ctypes.data, cap, nbytes.ctypes.data)
+    return dict(rc=rc, digests=[bytes(d) for d in digests[:n]], first=list(map(int, first[:n])), off=list(map(int, foff[:n])),
+                len=list(map(int, flen[:n])), frames=bytes(frames[: int(nbytes[0])]))

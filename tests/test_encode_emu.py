@@ -1,0 +1,117 @@
+"""K2/K3 encoder + pack bookkeeping on the SIMT emulator.  GPU-made frames must be valid Zstandard
+that the reference decoder (libzstd 1.5.5, one-shot AND the reference's streaming call sequence)
+restores byte-identically; dedup decisions, offsets and digests must equal the reference path's."""
+import numpy as np
+import pytest
+
+from oracle import ref_path
+from tests.golden.recipes import RECIPES, make_input, text, rand
+from tests.helpers import compress2, pack_batch, unpack_batch
+
+
+def _check_frame(lib, data, frame):
+    assert ref_path.ref_decompress(frame, len(data)) == data  # libzstd one-shot
+    assert ref_path.ref_decompress_stream(b"\x00" * 5 + frame + b"tail", 5) == data  # zstd_iterator.rs call sequence
+    got, err, consumed, _ = ref_path.c_zstd_decompress_frame(frame, len(data))  # C restatement
+    assert err == 0 and got == data and consumed == len(frame)
+    assert ref_path.find_frame_compressed_size(frame) == len(frame)
+
+
+@pytest.mark.parametrize("name", list(RECIPES))
+def test_compress2_recipes(emu, name):
+    data = make_input(name)
+    for level in (1, 3):
+        frame = compress2(emu, data, level=level)
+        _check_frame(emu, data, frame)
+        assert len(frame) <= emu.zg_compress_bound(len(data))
+
+
+def test_compress2_known_answer_shapes(emu):
+    # empty / tiny inputs are single Raw blocks exactly like libzstd's
+    assert compress2(emu, b"").hex() == "28b52ffd2400010000" + "99e9d851"
+    assert compress2(emu, b"a").hex() == "28b52ffd2401090000" + "61" + "5b6e8ca9"
+    assert compress2(emu, b"hello world\n").hex() == "28b52ffd240c610000" + b"hello world\n".hex() + "8c6d7d20"
+    assert compress2(emu, b"a", checksum=False).hex() == "28b52ffd2001090000" + "61"
+
+
+def test_compress2_flags_and_errors(emu):
+    import ctypes as C
+
+    data = text(30000, 5)
+    f = compress2(emu, data, checksum=False, content_size=False)
+    _check_frame(emu, data, f)
+    c = emu.zg_cctx_create()
+    assert emu.zg_cctx_set_parameter(c, 201, 1) == 1  # returns the value set, like libzstd
+    assert emu.zg_get_error_code(emu.zg_cctx_set_parameter(c, 100, 99)) == 42
+    assert emu.zg_get_error_code(emu.zg_cctx_set_parameter(c, 9999, 1)) == 40
+    rnd = rand(5000, 1)
+    small = C.create_string_buffer(100)
+    assert emu.zg_get_error_code(emu.zg_compress2(c, small, 100, rnd, len(rnd))) == 70  # never overruns
+    assert small.raw[99:] == b"\x00"
+    emu.zg_cctx_free(c)
+
+
+def test_ratio_vs_reference_small_corpus(emu):
+    from zarc_b200 import corpus
+
+    c = corpus.c2_source_tree(total_bytes=600_000, seed=3)
+    blob = corpus.materialise_host(emu, c)
+    datas = [bytes(blob[int(o) : int(o) + int(l)]) for o, l in zip(c.off, c.len)]
+    ours = sum(len(compress2(emu, d)) for d in datas)
+    ref = sum(len(ref_path.ref_compress(d)) for d in datas)
+    ratio_ours, ratio_ref = c.total_bytes / ours, c.total_bytes / ref
+    print("ratio ours", ratio_ours, "ref L3", ratio_ref)
+    assert ratio_ours > 0.85 * ratio_ref
+
+
+def test_pack_batch_matches_reference_bookkeeping(emu):
+    files = [text(3000, 1), rand(2000, 2), text(3000, 1), b"", text(200_000, 4), b"", rand(2000, 2), text(10, 9)]
+    c = emu.zg_cctx_create()
+    emu.check(emu.zg_cctx_init(c, 0))
+    emu.check(emu.zg_cctx_set_parameter(c, 201, 1))
+    emu.check(emu.zg_cctx_reset_archive(c, 12))
+    r = pack_batch(emu, c, files)
+    assert r["rc"] == 0
+    # the reference path on the same ordered file list
+    out = bytearray()
+    enc = ref_path.RefEncoder(out, level=3)
+    ref_digests = [enc.add_data_frame(f) for f in files]
+    assert r["digests"] == ref_digests
+    seen, first = set(), []
+    for d in ref_digests:
+        first.append(0 if d in seen else 1)
+        seen.add(d)
+    assert r["first"] == first
+    # offsets: 12 + running sum of frame lengths in insertion order of unique contents
+    pos = 12
+    for i, f in enumerate(files):
+        if first[i]:
+            assert r["off"][i] == pos
+            frame = r["frames"][pos - 12 : pos - 12 + r["len"][i]]
+            _check_frame(emu, f, frame)
+            pos += r["len"][i]
+        else:
+            j = ref_digests.index(ref_digests[i])
+            assert (r["off"][i], r["len"][i]) == (r["off"][j], r["len"][j])
+    assert pos - 12 == len(r["frames"]) and emu.zg_cctx_archive_offset(c) == pos
+    # a second batch dedups against the first and continues the offsets
+    files2 = [rand(2000, 2), text(777, 7), text(777, 7)]
+    r2 = pack_batch(emu, c, files2)
+    assert r2["first"] == [0, 1, 0]
+    assert (r2["off"][0], r2["len"][0]) == (r["off"][1], r["len"][1])
+    assert r2["off"][1] == pos and r2["off"][2] == pos
+    _check_frame(emu, files2[1], r2["frames"])
+    # our own decoder restores the whole archive too
+    archive_frames = [r["frames"][o - 12 : o - 12 + l] for o, l, f1 in zip(r["off"], r["len"], first) if f1]
+    uniq = [f for f, f1 in zip(files, first) if f1]
+    outs, ok, status, rc = unpack_batch(emu, archive_frames, [len(f) for f in uniq], [d for d, f1 in zip(ref_digests, first) if f1])
+    assert rc == 0 and outs == uniq and all(ok)
+    emu.zg_cctx_free(c)
+
+
+def test_pack_batch_capacity_error(emu):
+    c = emu.zg_cctx_create()
+    emu.check(emu.zg_cctx_reset_archive(c, 12))
+    r = pack_batch(emu, c, [rand(5000, 3)], cap=100)
+    assert emu.zg_get_error_code(r["rc"]) == 70
+    emu.zg_cctx_free(c)

@@ -118,6 +118,46 @@ def main():
         res[f"unpack_verify_c2_L{args.level}_gbs"] = total / best / 1e6
         res["verify_all_ok"] = int(d_ok.sum()) == K
         lib.zg_dctx_free(dctx)
+    if "pack" in args.what:
+        cctx = lib.zg_cctx_create()
+        lib.zg_cctx_set_stream(cctx, s)
+        lib.check(lib.zg_cctx_init(cctx, 0))
+        lib.check(lib.zg_cctx_set_parameter(cctx, 201, 1))
+        lib.check(lib.zg_cctx_set_parameter(cctx, 100, args.level))
+        cap = c.total_bytes + c.total_bytes // 10 + 64 * n
+        d_dig = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        d_first = torch.empty(n, dtype=torch.uint8, device="cuda")
+        d_foff = torch.empty(n, dtype=torch.int64, device="cuda")
+        d_flen = torch.empty(n, dtype=torch.int64, device="cuda")
+        d_frames = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        nbytes = np.zeros(1, dtype=np.uint64)
+
+        def run_pack():
+            lib.check(lib.zg_cctx_reset_archive(cctx, 12))
+            lib.check(lib.zg_pack_batch_dev(cctx, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, d_dig.data_ptr(), d_first.data_ptr(),
+                                            d_foff.data_ptr(), d_flen.data_ptr(), d_frames.data_ptr(), cap, nbytes.ctypes.data))
+
+        best, med = timeit(run_pack, iters=3, warmup=1)
+        res[f"pack_c2_L{args.level}_gbs"] = c.total_bytes / best / 1e6
+        res["pack_ratio"] = c.total_bytes / float(nbytes[0])
+        res["pack_unique"] = int(d_first.sum())
+        # unpack what we packed
+        dctx = lib.zg_dctx_create()
+        lib.zg_dctx_set_stream(dctx, s)
+        d_out = torch.empty(c.blob_bytes + 64, dtype=torch.uint8, device="cuda")
+        d_ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        d_status = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_foff0 = d_foff - 12
+
+        def run_unpack():
+            lib.check(lib.zg_unpack_batch_dev(dctx, d_frames.data_ptr(), int(nbytes[0]), n, d_foff0.data_ptr(), d_flen.data_ptr(), ln.data_ptr(),
+                                              d_dig.data_ptr(), d_out.data_ptr(), c.blob_bytes, off.data_ptr(), d_ok.data_ptr(), d_status.data_ptr()))
+
+        best, med = timeit(run_unpack, iters=3, warmup=1)
+        res[f"unpack_own_c2_gbs"] = c.total_bytes / best / 1e6
+        res["roundtrip_ok"] = bool(int(d_ok.sum()) == n and torch.equal(d_out[: c.blob_bytes], blob[: c.blob_bytes]))
+        lib.zg_cctx_free(cctx)
+        lib.zg_dctx_free(dctx)
     print(json.dumps(res))
 
 

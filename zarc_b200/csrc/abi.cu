@@ -19,6 +19,7 @@ static int dev_count() {
 	}
 	return g_dev_count;
 }
+int zg_abi_dev_count() { return dev_count(); }
 int zg_sm_count() {
 	if (!g_sm_count) {
 		int d = 0;
@@ -518,20 +519,4 @@ size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* inp
 
 }  // extern "C"
 
-// ---- entry points still to be wired (return GENERIC until their kernels land) -----------------
-#ifndef ZG_HAVE_ENCODER
-extern "C" {
-zg_cctx* zg_cctx_create(void) { return nullptr; }
-void zg_cctx_free(zg_cctx*) {}
-size_t zg_cctx_init(zg_cctx*, int) { return ZG_ERR(ZG_error_GENERIC); }
-size_t zg_cctx_set_parameter(zg_cctx*, int, int) { return ZG_ERR(ZG_error_GENERIC); }
-size_t zg_cctx_reset(zg_cctx*, int) { return ZG_ERR(ZG_error_GENERIC); }
-size_t zg_cctx_set_stream(zg_cctx*, void*) { return ZG_ERR(ZG_error_GENERIC); }
-size_t zg_compress2(zg_cctx*, void*, size_t, const void*, size_t) { return ZG_ERR(ZG_error_GENERIC); }
-size_t zg_compress_bound(size_t n) { return n + (n >> 8) + 64; }
-size_t zg_cctx_reset_archive(zg_cctx*, uint64_t) { return ZG_ERR(ZG_error_GENERIC); }
-uint64_t zg_cctx_archive_offset(const zg_cctx*) { return 0; }
-size_t zg_pack_batch(zg_cctx*, const uint8_t*, const uint64_t*, const uint64_t*, uint64_t, uint8_t*, uint8_t*, uint64_t*, uint64_t*, uint8_t*, uint64_t, uint64_t*) { return ZG_ERR(ZG_error_GENERIC); }
-size_t zg_pack_batch_dev(zg_cctx*, const uint8_t*, const uint64_t*, const uint64_t*, uint64_t, uint8_t*, uint8_t*, uint64_t*, uint64_t*, uint8_t*, uint64_t, uint64_t*) { return ZG_ERR(ZG_error_GENERIC); }
-}
-#endif
+// the compression context and zg_pack_batch live in abi_pack.cu

@@ -1,0 +1,360 @@
+// C ABI, pack side: zg_cctx (CCtx analogue + the Encoder's content state), zg_pack_batch[_dev],
+// zg_compress2.  Host code here only moves buffers and does bookkeeping on counts/sizes.
+#include "common.h"
+#include <new>
+#include <vector>
+#include <string.h>
+
+int zg_abi_dev_count();  // abi.cu
+
+#define ZG_NEED_DEVICE() \
+	do {                 \
+		if (zg_abi_dev_count() <= 0) return ZG_ERR(ZG_error_no_device); \
+	} while (0)
+#define ZG_TRY(expr)              \
+	do {                          \
+		size_t r_ = (expr);       \
+		if (zg_is_error(r_)) return r_; \
+	} while (0)
+#define ZG_CUDA(expr) \
+	do {              \
+		if ((expr) != cudaSuccess) return ZG_ERR(ZG_error_device); \
+	} while (0)
+#define ZG_ALLOC(expr) \
+	do {               \
+		if ((expr) != cudaSuccess) return ZG_ERR(ZG_error_memory_allocation); \
+	} while (0)
+
+// pack.cu
+size_t zg_pk_dedup_insert(cudaStream_t s, const u8* g_digest, u64 lo, u64 hi, u32* table, u32 mask);
+size_t zg_pk_dedup_resolve(cudaStream_t s, const u8* g_digest, u64 base, u64 n, const u32* table, u32 mask, const u64* len, u64* rep,
+                           u8* first, u64* isfirst64, u64* nblk, u64* clen);
+size_t zg_pk_build_ulist(cudaStream_t s, const u8* first, const u64* uidx, const u64* blk_first, u64 n, u32* ulist, u64* blk_base,
+                         u64 nuniq, u64 nblocks);
+size_t zg_pk_block_out_sizes(cudaStream_t s, const u32* blk_csize, u64 nblocks, u64* blk_out);
+size_t zg_pk_frame_sizes(cudaStream_t s, const u32* ulist, const u64* blk_base, const u64* blk_pos, const u64* blk_total, const u64* len,
+                         u64 nuniq, u32 flags, u64* frame_len_u);
+size_t zg_pk_xxh64_list(cudaStream_t s, const u8* blob, const u64* off, const u64* len, const u32* ulist, u64 nuniq, u64* out);
+size_t zg_pk_frame_assemble(cudaStream_t s, const u8* blob, const u8* comp, const u64* file_off, const u64* comp_off, const u64* file_len,
+                            const u32* ulist, const u64* blk_base, const u64* blk_pos, const u32* blk_csize, const u64* frame_off_u,
+                            const u64* xxh, u64 nuniq, u64 nblocks, u32 flags, u64 archive_base, u8* frames_out);
+size_t zg_pk_record_answer(cudaStream_t s, const u32* ulist, const u64* frame_off_u, const u64* frame_len_u, u64 nuniq, u64 base,
+                           u64* g_off, u64* g_len, const u64* rep, u64 n, u64* frame_off, u64* frame_len);
+
+// The Encoder's content state: `frames: HashMap<Digest, Frame>` + `offset` (encode.rs:32,36)
+struct ZgArchive {
+	u64 offset = 0;
+	u64 nfiles = 0;  // global file ids issued so far
+	ZgBuf g_digest, g_off, g_len;
+	ZgBuf table;
+	u32 table_size = 0;
+	void release() {
+		g_digest.release();
+		g_off.release();
+		g_len.release();
+		table.release();
+		table_size = 0;
+		nfiles = 0;
+	}
+};
+
+struct zg_cctx {
+	cudaStream_t stream = 0;
+	bool own_stream = false;
+	int level = 3, checksum = 0, content_size = 1;
+	int other_params[16] = {0};
+	ZgArchive archive, oneshot;
+	ZgB3Work b3;
+	ZgZeWork ze;
+	ZgBuf tiles, rep, isfirst64, nblk, clen, uidx, blkfirst, comp_off, ulist, blk_base, blk_csize, blk_out, blk_pos, frame_len_u,
+	    frame_off_u, xxh, comp, totals, first_tmp;
+	ZgHostBuf h;
+	// host-API staging
+	ZgBuf d_blob, d_meta, d_out_meta, d_frames;
+};
+
+static cudaError_t grow_keep(ZgBuf& b, size_t need, size_t keep, cudaStream_t s) {
+	if (need <= b.cap) return cudaSuccess;
+	ZgBuf nb;
+	cudaError_t e = nb.reserve(need * 2);
+	if (e != cudaSuccess) return e;
+	if (keep && b.p) {
+		e = cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, s);
+		if (e != cudaSuccess) return e;
+		cudaStreamSynchronize(s);
+	}
+	b.release();
+	b = nb;
+	return cudaSuccess;
+}
+
+static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
+                        u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes) {
+	cudaStream_t s = c->stream;
+	if (frames_bytes) *frames_bytes = 0;
+	if (F == 0) return 0;
+	u64 base = A.nfiles;
+	if (base + F >= 0xfffffff0ull) return ZG_ERR(ZG_error_GENERIC);
+	// the map's storage, indexed by global file id
+	ZG_ALLOC(grow_keep(A.g_digest, (base + F) * 32, base * 32, s));
+	ZG_ALLOC(grow_keep(A.g_off, (base + F) * 8, base * 8, s));
+	ZG_ALLOC(grow_keep(A.g_len, (base + F) * 8, base * 8, s));
+	u8* g_digest = A.g_digest.as<u8>();
+	// (1) digests (content_frame.rs:26)
+	ZG_TRY(zg_blake3_run(s, c->b3, blob, off, len, F, g_digest + 32 * base));
+	if (digests_out) ZG_CUDA(cudaMemcpyAsync(digests_out, g_digest + 32 * base, F * 32, cudaMemcpyDeviceToDevice, s));
+	// (2) dedup (content_frame.rs:30): the table keeps, per digest, the smallest global id
+	u64 want = 1024;
+	while (want < 2 * (base + F)) want <<= 1;
+	if (want > A.table_size) {
+		A.table.release();
+		ZG_ALLOC(A.table.reserve(want * 4));
+		A.table_size = (u32)want;
+		ZG_CUDA(cudaMemsetAsync(A.table.p, 0, want * 4, s));
+		ZG_TRY(zg_pk_dedup_insert(s, g_digest, 0, base, A.table.as<u32>(), A.table_size - 1));
+	}
+	ZG_TRY(zg_pk_dedup_insert(s, g_digest, base, base + F, A.table.as<u32>(), A.table_size - 1));
+	ZG_ALLOC(c->rep.reserve(F * 8));
+	ZG_ALLOC(c->isfirst64.reserve(F * 8));
+	ZG_ALLOC(c->nblk.reserve(F * 8));
+	ZG_ALLOC(c->clen.reserve(F * 8));
+	ZG_ALLOC(c->uidx.reserve(F * 8));
+	ZG_ALLOC(c->blkfirst.reserve(F * 8));
+	ZG_ALLOC(c->comp_off.reserve(F * 8));
+	ZG_ALLOC(c->totals.reserve(64));
+	ZG_ALLOC(c->h.reserve(64));
+	u8* first = first_out;
+	if (!first) {
+		ZG_ALLOC(c->first_tmp.reserve(F));
+		first = c->first_tmp.as<u8>();
+	}
+	u64* totals = c->totals.as<u64>();
+	ZG_TRY(zg_pk_dedup_resolve(s, g_digest, base, F, A.table.as<u32>(), A.table_size - 1, len, c->rep.as<u64>(), first,
+	                           c->isfirst64.as<u64>(), c->nblk.as<u64>(), c->clen.as<u64>()));
+	ZG_TRY(zg_scan_run(s, c->tiles, c->isfirst64.as<u64>(), F, 0, c->uidx.as<u64>(), totals + 0));
+	ZG_TRY(zg_scan_run(s, c->tiles, c->nblk.as<u64>(), F, 0, c->blkfirst.as<u64>(), totals + 1));
+	ZG_TRY(zg_scan_run(s, c->tiles, c->clen.as<u64>(), F, 0, c->comp_off.as<u64>(), totals + 2));
+	u64* ht = c->h.as<u64>();
+	ZG_CUDA(cudaMemcpyAsync(ht, totals, 24, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	u64 nuniq = ht[0], nblocks = ht[1], comp_bytes = ht[2];
+	u32 flags = (c->checksum ? 1u : 0u) | (c->content_size ? 2u : 0u);
+	u64 new_offset = A.offset;
+	if (nuniq) {
+		ZG_ALLOC(c->ulist.reserve(nuniq * 4));
+		ZG_ALLOC(c->blk_base.reserve((nuniq + 1) * 8));
+		ZG_ALLOC(c->blk_csize.reserve(nblocks * 4));
+		ZG_ALLOC(c->blk_out.reserve(nblocks * 8));
+		ZG_ALLOC(c->blk_pos.reserve(nblocks * 8));
+		ZG_ALLOC(c->frame_len_u.reserve(nuniq * 8));
+		ZG_ALLOC(c->frame_off_u.reserve(nuniq * 8));
+		ZG_ALLOC(c->xxh.reserve(nuniq * 8));
+		ZG_ALLOC(c->comp.reserve(comp_bytes + 64));
+		ZG_TRY(zg_pk_build_ulist(s, first, c->uidx.as<u64>(), c->blkfirst.as<u64>(), F, c->ulist.as<u32>(), c->blk_base.as<u64>(), nuniq,
+		                         nblocks));
+		// (3) compress every new content (content_frame.rs:41 -> lowlevel_frames.rs:30)
+		ZG_TRY(zg_zstd_encode_run(s, c->ze, blob, off, c->comp_off.as<u64>(), len, c->ulist.as<u32>(), c->blk_base.as<u64>(), (u32)nuniq,
+		                          nblocks, c->comp.as<u8>(), c->blk_csize.as<u32>(), c->level));
+		if (c->checksum) ZG_TRY(zg_pk_xxh64_list(s, blob, off, len, c->ulist.as<u32>(), nuniq, c->xxh.as<u64>()));
+		// (4) frame lengths -> archive offsets (content_frame.rs:22,45)
+		ZG_TRY(zg_pk_block_out_sizes(s, c->blk_csize.as<u32>(), nblocks, c->blk_out.as<u64>()));
+		ZG_TRY(zg_scan_run(s, c->tiles, c->blk_out.as<u64>(), nblocks, 0, c->blk_pos.as<u64>(), totals + 3));
+		ZG_TRY(zg_pk_frame_sizes(s, c->ulist.as<u32>(), c->blk_base.as<u64>(), c->blk_pos.as<u64>(), totals + 3, len, nuniq, flags,
+		                         c->frame_len_u.as<u64>()));
+		ZG_TRY(zg_scan_run(s, c->tiles, c->frame_len_u.as<u64>(), nuniq, A.offset, c->frame_off_u.as<u64>(), totals + 4));
+		ZG_CUDA(cudaMemcpyAsync(ht + 4, totals + 4, 8, cudaMemcpyDeviceToHost, s));
+		ZG_CUDA(cudaStreamSynchronize(s));
+		new_offset = ht[4];
+		u64 bytes = new_offset - A.offset;
+		if (bytes > frames_cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
+		if (!frames_out) return ZG_ERR(ZG_error_dstBuffer_null);
+		// (5) write the frames in insertion order
+		ZG_TRY(zg_pk_frame_assemble(s, blob, c->comp.as<u8>(), off, c->comp_off.as<u64>(), len, c->ulist.as<u32>(), c->blk_base.as<u64>(),
+		                            c->blk_pos.as<u64>(), c->blk_csize.as<u32>(), c->frame_off_u.as<u64>(), c->xxh.as<u64>(), nuniq,
+		                            nblocks, flags, A.offset, frames_out));
+		if (frames_bytes) *frames_bytes = bytes;
+	}
+	// (6) Frame records (content_frame.rs:48-57) and per-file answers
+	ZG_TRY(zg_pk_record_answer(s, c->ulist.as<u32>(), c->frame_off_u.as<u64>(), c->frame_len_u.as<u64>(), nuniq, base, A.g_off.as<u64>(),
+	                           A.g_len.as<u64>(), c->rep.as<u64>(), F, frame_off_out, frame_len_out));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	ZG_CUDA(cudaGetLastError());
+	A.nfiles = base + F;
+	A.offset = new_offset;
+	return 0;
+}
+
+extern "C" {
+
+zg_cctx* zg_cctx_create(void) {
+	if (zg_abi_dev_count() <= 0) return nullptr;
+	zg_cctx* c = new (std::nothrow) zg_cctx();
+	if (!c) return nullptr;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		delete c;
+		return nullptr;
+	}
+	c->own_stream = true;
+	return c;
+}
+void zg_cctx_free(zg_cctx* c) {
+	if (!c) return;
+	cudaStreamSynchronize(c->stream);
+	c->archive.release();
+	c->oneshot.release();
+	zg_b3work_free(c->b3);
+	c->ze.scratch.release();
+	c->ze.queue.release();
+	for (ZgBuf* b : {&c->tiles, &c->rep, &c->isfirst64, &c->nblk, &c->clen, &c->uidx, &c->blkfirst, &c->comp_off, &c->ulist, &c->blk_base,
+	                 &c->blk_csize, &c->blk_out, &c->blk_pos, &c->frame_len_u, &c->frame_off_u, &c->xxh, &c->comp, &c->totals, &c->first_tmp,
+	                 &c->d_blob, &c->d_meta, &c->d_out_meta, &c->d_frames})
+		b->release();
+	c->h.release();
+	if (c->own_stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+size_t zg_cctx_set_stream(zg_cctx* c, void* stream) {
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	if (c->own_stream) cudaStreamDestroy(c->stream);
+	c->own_stream = false;
+	c->stream = (cudaStream_t)stream;
+	return 0;
+}
+// CCtx::init(level) == ZSTD_initCStream(cctx, level): session reset + compressionLevel (encode.rs:62)
+size_t zg_cctx_init(zg_cctx* c, int level) {
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	if (level < -131072 || level > 22) return ZG_ERR(ZG_error_parameter_outOfBound);
+	c->level = level == 0 ? 3 : level;
+	return 0;
+}
+size_t zg_cctx_set_parameter(zg_cctx* c, int param, int value) {
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	switch (param) {
+	case ZG_c_compressionLevel:
+		if (value < -131072 || value > 22) return ZG_ERR(ZG_error_parameter_outOfBound);
+		c->level = value == 0 ? 3 : value;
+		return (size_t)(value < 0 ? 0 : value);
+	case ZG_c_checksumFlag:
+		c->checksum = value != 0;
+		return (size_t)c->checksum;
+	case ZG_c_contentSizeFlag:
+		c->content_size = value != 0;
+		return (size_t)c->content_size;
+	case ZG_c_dictIDFlag:
+		return (size_t)(value != 0);
+	case ZG_c_windowLog:
+		if (value != 0 && (value < 10 || value > 31)) return ZG_ERR(ZG_error_parameter_outOfBound);
+		c->other_params[param - 100] = value;
+		return (size_t)value;
+	case ZG_c_hashLog:
+	case ZG_c_chainLog:
+	case ZG_c_searchLog:
+	case ZG_c_minMatch:
+	case ZG_c_targetLength:
+	case ZG_c_strategy:
+		// accepted for CLI compatibility (pack.rs:140-195); the GPU match finder has its own tuning
+		if (value < 0) return ZG_ERR(ZG_error_parameter_outOfBound);
+		c->other_params[param - 100] = value;
+		return (size_t)value;
+	default:
+		return ZG_ERR(ZG_error_parameter_unsupported);
+	}
+}
+size_t zg_cctx_reset(zg_cctx* c, int directive) {
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	if (directive < 1 || directive > 3) return ZG_ERR(ZG_error_parameter_outOfBound);
+	// session_only: nothing is in flight between calls (content_frame.rs:37-39 does this per frame)
+	if (directive & ZG_reset_parameters) {
+		c->level = 3;
+		c->checksum = 0;
+		c->content_size = 1;
+		memset(c->other_params, 0, sizeof c->other_params);
+	}
+	return 0;
+}
+size_t zg_cctx_reset_archive(zg_cctx* c, uint64_t first_frame_offset) {
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	cudaStreamSynchronize(c->stream);
+	c->archive.nfiles = 0;
+	c->archive.offset = first_frame_offset;
+	if (c->archive.table_size) ZG_CUDA(cudaMemsetAsync(c->archive.table.p, 0, (size_t)c->archive.table_size * 4, c->stream));
+	return 0;
+}
+uint64_t zg_cctx_archive_offset(const zg_cctx* c) { return c ? c->archive.offset : 0; }
+size_t zg_compress_bound(size_t n) { return n + (n >> 8) + (n < (128 << 10) ? (((128 << 10) - n) >> 11) : 0); }  // ZSTD_compressBound
+
+size_t zg_pack_batch_dev(zg_cctx* c, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n, uint8_t* digests,
+                         uint8_t* first, uint64_t* frame_off, uint64_t* frame_len, uint8_t* frames_out, uint64_t frames_cap,
+                         uint64_t* frames_bytes) {
+	ZG_NEED_DEVICE();
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	return pack_core(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes);
+}
+
+static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n,
+                        uint8_t* digests, uint8_t* first, uint64_t* frame_off, uint64_t* frame_len, uint8_t* frames_out,
+                        uint64_t frames_cap, uint64_t* frames_bytes) {
+	cudaStream_t s = c->stream;
+	if (frames_bytes) *frames_bytes = 0;
+	if (n == 0) return 0;
+	u64 lo = ~0ull, hi = 0;
+	for (u64 i = 0; i < n; i++) {
+		lo = off[i] < lo ? off[i] : lo;
+		hi = off[i] + len[i] > hi ? off[i] + len[i] : hi;
+	}
+	u64 span = hi - lo;
+	ZG_ALLOC(c->d_blob.reserve(span + 64));
+	ZG_ALLOC(c->d_meta.reserve(n * 16));
+	ZG_ALLOC(c->d_out_meta.reserve(n * 49 + 64));
+	ZG_ALLOC(c->d_frames.reserve(frames_cap + 64));
+	std::vector<u64> rebased(n);
+	for (u64 i = 0; i < n; i++) rebased[i] = off[i] - lo;
+	u64* m = c->d_meta.as<u64>();
+	if (span) ZG_CUDA(cudaMemcpyAsync(c->d_blob.p, blob + lo, span, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m, rebased.data(), n * 8, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaMemcpyAsync(m + n, len, n * 8, cudaMemcpyHostToDevice, s));
+	ZG_CUDA(cudaStreamSynchronize(s));  // `rebased` is pageable
+	u8* o = c->d_out_meta.as<u8>();
+	u64* d_foff = (u64*)o;
+	u64* d_flen = d_foff + n;
+	u8* d_dig = (u8*)(d_flen + n);
+	u8* d_first = d_dig + n * 32;
+	u64 bytes = 0;
+	ZG_TRY(pack_core(c, A, c->d_blob.as<u8>(), m, m + n, n, d_dig, d_first, d_foff, d_flen, c->d_frames.as<u8>(), frames_cap, &bytes));
+	if (digests) ZG_CUDA(cudaMemcpyAsync(digests, d_dig, n * 32, cudaMemcpyDeviceToHost, s));
+	if (first) ZG_CUDA(cudaMemcpyAsync(first, d_first, n, cudaMemcpyDeviceToHost, s));
+	if (frame_off) ZG_CUDA(cudaMemcpyAsync(frame_off, d_foff, n * 8, cudaMemcpyDeviceToHost, s));
+	if (frame_len) ZG_CUDA(cudaMemcpyAsync(frame_len, d_flen, n * 8, cudaMemcpyDeviceToHost, s));
+	if (bytes) ZG_CUDA(cudaMemcpyAsync(frames_out, c->d_frames.p, bytes, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(cudaStreamSynchronize(s));
+	if (frames_bytes) *frames_bytes = bytes;
+	return 0;
+}
+
+size_t zg_pack_batch(zg_cctx* c, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n, uint8_t* digests,
+                     uint8_t* first, uint64_t* frame_off, uint64_t* frame_len, uint8_t* frames_out, uint64_t frames_cap,
+                     uint64_t* frames_bytes) {
+	ZG_NEED_DEVICE();
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	return pack_host(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes);
+}
+
+// CCtx::compress2 (lowlevel_frames.rs:30): one complete frame, no dedup, no archive state.
+size_t zg_compress2(zg_cctx* c, void* dst, size_t cap, const void* src, size_t n) {
+	ZG_NEED_DEVICE();
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	if (!dst) return ZG_ERR(ZG_error_dstBuffer_null);
+	ZgArchive& A = c->oneshot;
+	cudaStreamSynchronize(c->stream);
+	A.nfiles = 0;
+	A.offset = 0;
+	if (A.table_size) ZG_CUDA(cudaMemsetAsync(A.table.p, 0, (size_t)A.table_size * 4, c->stream));
+	uint64_t off = 0, len = n, bytes = 0;
+	static const uint8_t empty = 0;
+	size_t r = pack_host(c, A, src ? (const uint8_t*)src : &empty, &off, &len, 1, nullptr, nullptr, nullptr, nullptr, (uint8_t*)dst, cap,
+	                     &bytes);
+	if (zg_is_error(r)) return r;
+	return bytes;
+}
+
+}  // extern "C"

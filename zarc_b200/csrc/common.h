@@ -88,3 +88,12 @@ size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off,
                               const u32* cksums, u32* status, u64 n, int verify);
 size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n);
 size_t zg_first_error_run(cudaStream_t s, const u32* status, u64 n, u64* first);
+
+// ---- zstd_encode.cu ----
+struct ZgZeWork {
+	ZgBuf scratch;  // per-warp sequence/literal staging
+	ZgBuf queue;
+};
+size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
+                          const u32* ulist,
+                          const u64* blk_base, u32 nuniq, u64 nblocks, u8* comp, u32* blk_csize, int level);

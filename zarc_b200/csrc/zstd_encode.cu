@@ -1,0 +1,955 @@
+// K2 + K3: Zstandard block encode.  Replaces the arithmetic of CCtx::compress2 as called at
+// crates/zarc/src/encode/lowlevel_frames.rs:30 (libzstd 1.5.5 in the reference).  Compressed bytes
+// are not required to equal libzstd's; every block must be valid RFC 8878 that libzstd restores.
+//
+// One warp per <=128 KiB block, pulled from an atomic queue.
+//   K2 match finding: the warp hashes 32 consecutive positions at a time (4-byte hash) against a
+//      shared-memory table of 16-bit positions (64 KiB window inside the block), also matching
+//      lanes against each other (__match_any_sync) for distances < 32; every lane verifies and
+//      extends its own candidate; a warp-uniform greedy+lazy parse picks the matches, resolves
+//      repeat-offset codes and gathers literals (histogrammed in shared memory on the way).
+//   K3 entropy: length-limited Huffman for literals (tree description FSE-compressed or direct,
+//      1 or 4 streams, bit-packing parallel across the warp); FSE for LL/OF/ML codes with
+//      Predefined / RLE / FSE_Compressed modes; sequence bitstream written by lane 0.
+// Output: the block body in the block's slot of a scratch blob laid out like the input; block
+// sizes go to blk_csize (bit 31 = Raw block: body is the input itself).
+#include "common.h"
+#include "zstd_common.cuh"
+
+#define ZE_WARPS 4
+#define ZE_HLOG_MAX 13
+#define ZE_MAXSEQ 32768u
+#define ZE_MINMATCH 4u
+#define ZE_LANE_CAP 64u   // per-lane match extension cap; longer matches are extended by the whole warp
+#define ZE_RAW 0x80000000u
+
+ZG_CONST_TABLE u8 ZS_LL_CODE[64] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 20, 20, 21, 21, 21, 21, 22, 22, 22, 22, 22, 22, 22, 22, 23, 23, 23, 23, 23, 23, 23, 23, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24};
+ZG_CONST_TABLE u8 ZS_ML_CODE[128] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 36, 37, 37, 37, 37, 38, 38, 38, 38, 38, 38, 38, 38, 39, 39, 39, 39, 39, 39, 39, 39, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 40, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 41, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42, 42};
+
+ZG_DEV u32 ze_ll_code(u32 ll) { return ll < 64 ? ZS_LL_CODE[ll] : zs_highbit(ll) + 19; }
+ZG_DEV u32 ze_ml_code(u32 mlbase) { return mlbase < 128 ? ZS_ML_CODE[mlbase] : zs_highbit(mlbase) + 36; }
+
+// per-warp global scratch
+struct ZeScratch {
+	u32 ll[ZE_MAXSEQ];
+	u32 ml[ZE_MAXSEQ];
+	u32 ofb[ZE_MAXSEQ];   // offBase: 1..3 repeat codes, else offset + 3
+	u32 codes[ZE_MAXSEQ]; // ll | ml << 8 | of << 16
+	u8 lit[ZS_BLOCK_MAX + 64];
+};
+
+struct ZeEnt {
+	u16 hcode[256];       // Huffman code | nbBits << 11
+	u8 hweight[256];
+	u16 sorted_sym[256];
+	u32 sorted_cnt[256];
+	u32 node_cnt[512];
+	u16 node_par[512];
+	u8 node_depth[512];
+	u16 st[3][512];       // FSE state tables: LL, ML, OF (OF also serves the Huffman-weight table)
+	u32 dnb[3][64];       // symbolTT.deltaNbBits
+	i32 dfs[3][64];       // symbolTT.deltaFindState
+	u32 hist3[3][64];
+	i16 norm[64];
+	u16 cumul[66];
+	u8 tsym[512];
+	u8 wdesc[192];        // Huffman tree description staging
+	u32 window[96];       // bit-packing window (384 B)
+};
+struct ZeWarp {
+	union {
+		u16 htab[1 << ZE_HLOG_MAX];
+		ZeEnt e;
+	} u;
+	u32 hist[256];
+	u32 misc[16];
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward bit writer (LSB first), single lane, bounded
+struct ZeBitW {
+	u8* p;
+	u8* end;
+	u64 acc;
+	u32 nbits;
+	bool ovf;
+};
+ZG_DEV void ze_bw_init(ZeBitW& w, u8* p, u8* end) {
+	w.p = p;
+	w.end = end;
+	w.acc = 0;
+	w.nbits = 0;
+	w.ovf = false;
+}
+ZG_DEV void ze_bw_flush(ZeBitW& w) {
+	while (w.nbits >= 8) {
+		if (w.p < w.end) *w.p++ = (u8)w.acc;
+		else w.ovf = true;
+		w.acc >>= 8;
+		w.nbits -= 8;
+	}
+}
+ZG_DEV void ze_bw_add(ZeBitW& w, u32 v, u32 nb) {  // nb <= 32
+	if (w.nbits + nb > 56) ze_bw_flush(w);
+	w.acc |= (u64)(v & (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u))) << w.nbits;
+	w.nbits += nb;
+}
+// append the end marker and pad; returns one-past-last byte written
+ZG_DEV u8* ze_bw_close(ZeBitW& w) {
+	ze_bw_add(w, 1, 1);
+	ze_bw_flush(w);
+	if (w.nbits) {
+		if (w.p < w.end) *w.p++ = (u8)w.acc;
+		else w.ovf = true;
+		w.nbits = 0;
+	}
+	return w.p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FSE compression tables (libzstd's formulation: state table + per-symbol deltaNbBits/deltaFindState)
+struct ZeCT {
+	u16* st;
+	u32* dnb;
+	i32* dfs;
+	u32 log;
+};
+ZG_DEV u32 ze_fse_init_state(const ZeCT& ct, u32 sym) {  // FSE_initCState2: smallest state of sym
+	u32 d = ct.dnb[sym];
+	u32 nb = (d + (1u << 15)) >> 16;
+	u32 v = (nb << 16) - d;
+	return ct.st[(v >> nb) + ct.dfs[sym]];
+}
+ZG_DEV void ze_fse_encode(ZeBitW& w, const ZeCT& ct, u32& state, u32 sym) {
+	u32 nb = (state + ct.dnb[sym]) >> 16;
+	ze_bw_add(w, state, nb);
+	state = ct.st[(state >> nb) + ct.dfs[sym]];
+}
+ZG_DEV void ze_fse_flush_state(ZeBitW& w, const ZeCT& ct, u32 state) { ze_bw_add(w, state, ct.log); }
+
+// single lane.  norm may hold -1 ("less than one") entries: only the predefined tables do.
+ZG_DEV void ze_fse_build_ctable(const ZeCT& ct, const i16* norm, u32 maxsym, u8* tsym, u16* cumul) {
+	u32 log = ct.log, size = 1u << log;
+	u32 high = size - 1;
+	cumul[0] = 0;
+	for (u32 s = 1; s <= maxsym + 1; s++) {
+		i32 n = norm[s - 1];
+		if (n == -1) {
+			cumul[s] = (u16)(cumul[s - 1] + 1);
+			tsym[high--] = (u8)(s - 1);
+		} else {
+			cumul[s] = (u16)(cumul[s - 1] + n);
+		}
+	}
+	u32 step = (size >> 1) + (size >> 3) + 3, mask = size - 1, pos = 0;
+	for (u32 s = 0; s <= maxsym; s++)
+		for (i32 i = 0; i < norm[s]; i++) {
+			tsym[pos] = (u8)s;
+			do {
+				pos = (pos + step) & mask;
+			} while (pos > high);
+		}
+	for (u32 u = 0; u < size; u++) {
+		u32 s = tsym[u];
+		ct.st[cumul[s]++] = (u16)(size + u);
+	}
+	u32 total = 0;
+	for (u32 s = 0; s <= maxsym; s++) {
+		i32 n = norm[s];
+		if (n == 0) {
+			ct.dnb[s] = ((log + 1) << 16) - size;
+			ct.dfs[s] = 0;
+		} else if (n == 1 || n == -1) {
+			ct.dnb[s] = (log << 16) - size;
+			ct.dfs[s] = (i32)total - 1;
+			total += 1;
+		} else {
+			u32 maxbits = log - zs_highbit((u32)n - 1);
+			u32 minstate = (u32)n << maxbits;
+			ct.dnb[s] = (maxbits << 16) - minstate;
+			ct.dfs[s] = (i32)total - n;
+			total += (u32)n;
+		}
+	}
+}
+// libzstd's FSE_optimalTableLog
+ZG_DEV u32 ze_fse_table_log(u32 maxlog, u32 total, u32 maxsym) {
+	u32 maxbits_src = zs_highbit(total - 1) - 2;
+	u32 minbits = zg_min<u32>(zs_highbit(total) + 1, zs_highbit(maxsym) + 2);
+	u32 log = maxlog;
+	if (maxbits_src < log) log = maxbits_src;
+	if (minbits > log) log = minbits;
+	if (log < 5) log = 5;
+	if (log > maxlog) log = maxlog;
+	return log;
+}
+// counts -> normalized counts summing to 2^log, every present symbol >= 1.  Single lane.
+ZG_DEV void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 maxsym, u32 log) {
+	u32 size = 1u << log;
+	i32 left = (i32)size;
+	u32 largest = 0, largest_p = 0;
+	for (u32 s = 0; s <= maxsym; s++) {
+		u32 c = cnt[s];
+		if (c == 0) {
+			norm[s] = 0;
+			continue;
+		}
+		u64 scaled = ((u64)c << log);
+		u32 p = (u32)(scaled / total);
+		u32 rem = (u32)(scaled - (u64)p * total);
+		if (p == 0) p = 1;
+		else if (p < 8 && rem * 2 > total) p++;  // round small probabilities to nearest
+		if (p > largest_p) {
+			largest_p = p;
+			largest = s;
+		}
+		norm[s] = (i16)p;
+		left -= (i32)p;
+	}
+	if (left >= 0 || -left < (norm[largest] >> 1)) {
+		norm[largest] = (i16)(norm[largest] + left);
+		return;
+	}
+	// rare: too many forced-to-1 symbols.  Take the excess from the largest entries, one at a time.
+	while (left < 0) {
+		u32 big = 0;
+		for (u32 s = 1; s <= maxsym; s++)
+			if (norm[s] > norm[big]) big = s;
+		norm[big]--;
+		left++;
+	}
+}
+// FSE table description (NCount) writer, inverse of zs_read_ncount.  Single lane.  Returns bytes (0 = no room).
+ZG_DEV u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 maxsym, u32 log) {
+	ZeBitW w;
+	ze_bw_init(w, dst, dst + cap);
+	ze_bw_add(w, log - 5, 4);
+	i32 remaining = 1 << log;
+	u32 s = 0;
+	while (remaining > 0 && s <= maxsym) {
+		u32 bits = zs_highbit((u32)remaining + 1) + 1;
+		u32 thr = (1u << bits) - 1u - ((u32)remaining + 1u);
+		u32 value = (u32)(norm[s] + 1);
+		if (value < thr) {
+			ze_bw_add(w, value, bits - 1);
+		} else {
+			u32 v = value < (1u << (bits - 1)) ? value : value + thr;
+			ze_bw_add(w, v, bits);
+		}
+		remaining -= norm[s];
+		bool zero = norm[s] == 0;
+		s++;
+		if (zero) {
+			// count the zero symbols that follow, in 2-bit groups (3 = "three more, keep going")
+			u32 run = 0;
+			while (s + run <= maxsym && norm[s + run] == 0) run++;
+			s += run;
+			while (run >= 3) {
+				ze_bw_add(w, 3, 2);
+				run -= 3;
+			}
+			ze_bw_add(w, run, 2);
+		}
+	}
+	ze_bw_flush(w);
+	if (w.nbits) {
+		if (w.p < w.end) *w.p++ = (u8)w.acc;
+		else w.ovf = true;
+	}
+	return w.ovf ? 0 : (u32)(w.p - dst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Huffman: code lengths (<= 11 bits) from the literal histogram.  Returns maxBits (0 = failure),
+// fills e.hweight[0..maxsym], e.hcode[], *maxsym_out.  All lanes call.
+ZG_DEV u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
+	ZeEnt& e = W->u.e;
+	u32 lane = zg_lane();
+	// present symbols, ascending symbol order -> node_cnt/node_par as (cnt, sym) staging
+	u32 n = 0;
+	for (u32 k = 0; k < 8; k++) {
+		u32 s = k * 32 + lane;
+		u32 c = W->hist[s];
+		u32 b = __ballot_sync(ZG_FULL, c > 0);
+		if (c > 0) {
+			u32 idx = n + (u32)__popc(b & zg_lanemask_lt());
+			e.node_cnt[256 + idx] = c;
+			e.node_par[256 + idx] = (u16)s;
+		}
+		n += (u32)__popc(b);
+		e.hweight[s] = 0;
+	}
+	__syncwarp();
+	if (n < 2) return 0;
+	u32 maxsym = e.node_par[256 + n - 1];
+	// rank sort by (count, symbol)
+	for (u32 i = lane; i < n; i += 32) {
+		u32 key = (e.node_cnt[256 + i] << 8) | e.node_par[256 + i];
+		u32 rank = 0;
+		for (u32 j = 0; j < n; j++) rank += ((e.node_cnt[256 + j] << 8) | e.node_par[256 + j]) < key;
+		e.sorted_cnt[rank] = key >> 8;
+		e.sorted_sym[rank] = (u16)(key & 0xff);
+	}
+	__syncwarp();
+	if (lane == 0) {
+		u32 maxd = 0;
+		for (u32 limit = 1;; limit <<= 1) {
+			for (u32 i = 0; i < n; i++) e.node_cnt[i] = zg_max<u32>(e.sorted_cnt[i], limit);
+			u32 q1 = 0, q2 = n, nn = n;
+			while (nn < 2 * n - 1) {
+				u32 a, b;
+				if (q1 < n && (q2 >= nn || e.node_cnt[q1] <= e.node_cnt[q2])) a = q1++;
+				else a = q2++;
+				if (q1 < n && (q2 >= nn || e.node_cnt[q1] <= e.node_cnt[q2])) b = q1++;
+				else b = q2++;
+				e.node_cnt[nn] = e.node_cnt[a] + e.node_cnt[b];
+				e.node_par[a] = (u16)nn;
+				e.node_par[b] = (u16)nn;
+				nn++;
+			}
+			e.node_depth[2 * n - 2] = 0;
+			maxd = 0;
+			for (i32 k = (i32)(2 * n - 3); k >= 0; k--) {
+				u32 d = e.node_depth[e.node_par[k]] + 1u;
+				e.node_depth[k] = (u8)d;
+				if ((u32)k < n && d > maxd) maxd = d;
+			}
+			if (maxd <= ZS_HUF_MAXLOG) break;
+		}
+		// weights and canonical codes (ascending weight, then ascending symbol: RFC 8878 §4.2.1)
+		u32 rank[13];
+		for (u32 w = 0; w < 13; w++) rank[w] = 0;
+		for (u32 i = 0; i < n; i++) {
+			u32 w = maxd + 1 - e.node_depth[i];
+			e.hweight[e.sorted_sym[i]] = (u8)w;
+			rank[w]++;
+		}
+		u32 next[13];
+		u32 start = 0;
+		for (u32 w = 1; w <= maxd; w++) {
+			next[w] = start >> (w - 1);
+			start += rank[w] << (w - 1);
+		}
+		for (u32 s = 0; s <= maxsym; s++) {
+			u32 w = e.hweight[s];
+			if (w) {
+				u32 nb = maxd + 1 - w;
+				e.hcode[s] = (u16)(next[w]++ | (nb << 11));
+			}
+		}
+		W->misc[0] = maxd;
+	}
+	__syncwarp();
+	*maxsym_out = maxsym;
+	return W->misc[0];
+}
+
+// Huffman tree description into e.wdesc (single lane).  Returns its size, 0 if not representable.
+ZG_DEV u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
+	ZeEnt& e = W->u.e;
+	u32 nw = maxsym;  // weights 0..maxsym-1 are explicit, the last is implied
+	u32 direct = nw <= 128 ? 1 + ((nw + 1) >> 1) : 0;
+	u32 fse_size = 0;
+	if (nw > 2) {
+		u32 cnt[13];
+		for (u32 i = 0; i < 13; i++) cnt[i] = 0;
+		u32 maxw = 0, maxc = 0;
+		for (u32 i = 0; i < nw; i++) {
+			u32 w = e.hweight[i];
+			cnt[w]++;
+			if (w > maxw) maxw = w;
+		}
+		for (u32 i = 0; i <= maxw; i++) maxc = zg_max<u32>(maxc, cnt[i]);
+		if (maxc != nw && maxc > 1) {
+			u32 log = ze_fse_table_log(6, nw, maxw);
+			ze_fse_normalize(e.norm, cnt, nw, maxw, log);
+			u32 nc = ze_fse_write_ncount(e.wdesc + 1, 127, e.norm, maxw, log);
+			if (nc) {
+				ZeCT ct{e.st[2], e.dnb[2], e.dfs[2], log};
+				ze_fse_build_ctable(ct, e.norm, maxw, e.tsym, e.cumul);
+				ZeBitW bw;
+				ze_bw_init(bw, e.wdesc + 1 + nc, e.wdesc + 128);
+				u32 ip = nw, s1, s2;
+				// libzstd FSE_compress_usingCTable order: the last two weights seed the two states
+				if (nw & 1) {
+					s1 = ze_fse_init_state(ct, e.hweight[--ip]);
+					s2 = ze_fse_init_state(ct, e.hweight[--ip]);
+					ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
+				} else {
+					s2 = ze_fse_init_state(ct, e.hweight[--ip]);
+					s1 = ze_fse_init_state(ct, e.hweight[--ip]);
+				}
+				while (ip > 0) {
+					ze_fse_encode(bw, ct, s2, e.hweight[--ip]);
+					ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
+				}
+				ze_fse_flush_state(bw, ct, s2);
+				ze_fse_flush_state(bw, ct, s1);
+				u8* endp = ze_bw_close(bw);
+				u32 csz = (u32)(endp - (e.wdesc + 1));
+				if (!bw.ovf && csz < 128) fse_size = 1 + csz;
+			}
+		}
+	}
+	if (fse_size && (direct == 0 || fse_size < direct)) {
+		e.wdesc[0] = (u8)(fse_size - 1);
+		return fse_size;
+	}
+	if (!direct) return 0;
+	e.wdesc[0] = (u8)(127 + nw);
+	for (u32 i = 0; i < nw; i += 2) {
+		u32 hi = e.hweight[i], lo = i + 1 < nw ? e.hweight[i + 1] : 0;
+		e.wdesc[1 + (i >> 1)] = (u8)((hi << 4) | lo);
+	}
+	return direct;
+}
+
+// total code bits of lit[0..m)
+ZG_DEV u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
+	u32 bits = 0;
+	for (u32 i = zg_lane(); i < m; i += 32) bits += e.hcode[lit[i]] >> 11;
+	return zg_warp_sum(bits);
+}
+
+// One Huffman stream for lit[0..m) into dst (exactly `nbytes` bytes, as computed from count_bits).
+// The last literal is written first (lowest bits); parallel bit packing through a shared window.
+ZG_DEV void ze_huf_encode_stream(ZeWarp* W, const u8* lit, u32 m, u8* dst, u32 total_bits) {
+	ZeEnt& e = W->u.e;
+	u32 lane = zg_lane();
+	u32* win = e.window;  // 96 words
+	u32 bitpos = 0;       // bits already flushed to dst (multiple of 8) + bits pending in window
+	u32 flushed = 0;      // bytes written to dst
+	for (u32 i = lane; i < 96; i += 32) win[i] = 0;
+	__syncwarp();
+	// chunks of 32 lanes x 4 literals, walking from the end of the segment
+	for (u32 done = 0; done < m || done == 0; done += 128) {
+		// lane handles literals at reverse indices r = done + 4*lane + k  (r = 0 is the last literal)
+		u64 acc = 0;
+		u32 nb = 0;
+		for (u32 k = 0; k < 4; k++) {
+			u32 r = done + 4 * lane + k;
+			if (r < m) {
+				u32 c = e.hcode[lit[m - 1 - r]];
+				acc |= (u64)(c & 0x7ff) << nb;
+				nb += c >> 11;
+			}
+		}
+		bool is_last = done + 128 >= m;
+		u32 incl = zg_warp_incl_scan(nb);
+		u32 chunk_bits = __shfl_sync(ZG_FULL, incl, 31);
+		u32 start = (bitpos & 7) + incl - nb;  // bit offset inside the window
+		if (is_last && lane == 31) {
+			// the end marker follows the first literal's code
+			acc |= (u64)1 << nb;
+			nb += 1;
+		}
+		if (nb) {
+			u32 wi = start >> 5, sh = start & 31;
+			u64 lo = acc << sh;
+			atomicOr(&win[wi], (u32)lo);
+			u32 mid = (u32)(lo >> 32);
+			if (mid) atomicOr(&win[wi + 1], mid);
+			if (sh) {
+				u32 hi = (u32)(acc >> (64 - sh));
+				if (hi) atomicOr(&win[wi + 2], hi);
+			}
+		}
+		__syncwarp();
+		u32 wbits = (bitpos & 7) + chunk_bits + (is_last ? 1 : 0);
+		u32 nbytes = is_last ? (wbits + 7) >> 3 : wbits >> 3;
+		for (u32 i = lane; i < nbytes; i += 32) dst[flushed + i] = (u8)(win[i >> 2] >> (8 * (i & 3)));
+		__syncwarp();
+		// keep the partial byte, clear the rest
+		u32 keep = (wbits & 7) && !is_last ? (win[nbytes >> 2] >> (8 * (nbytes & 3))) & 0xff : 0;
+		__syncwarp();
+		for (u32 i = lane; i < 96; i += 32) win[i] = 0;
+		__syncwarp();
+		if (lane == 0) win[0] = keep;
+		__syncwarp();
+		flushed += nbytes;
+		bitpos += chunk_bits;
+		if (is_last) break;
+	}
+	(void)total_bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sequence tables: mode choice (libzstd's heuristic for fast strategies), description, CTable.
+// Single lane.  Writes the description at *pp (bounded by end).  Returns mode, or 0xff on overflow.
+ZG_DEV u32 ze_seq_table(ZeEnt& e, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u32 maxlog, u32 deflog, const i16* defnorm,
+                        u32 defmax, u8*& p, u8* end, ZeCT& ct) {
+	u32 most = 0, most_sym = 0;
+	for (u32 s = 0; s <= maxsym; s++)
+		if (cnt[s] > most) {
+			most = cnt[s];
+			most_sym = s;
+		}
+	ct.st = e.st[t];
+	ct.dnb = e.dnb[t];
+	ct.dfs = e.dfs[t];
+	if (most == nseq && nseq > 2) {  // RLE_Mode
+		if (p >= end) return 0xff;
+		*p++ = (u8)most_sym;
+		ct.log = 0;
+		ct.st[0] = 1;  // a 1-entry table: state never changes, no bits
+		for (u32 s = 0; s <= maxsym; s++) {
+			ct.dnb[s] = 0;
+			ct.dfs[s] = 0;
+		}
+		ct.dnb[most_sym] = 0u - 1u;  // (0 << 16) - (1 << 0): nbBits = (1 + dnb) >> 16 = 0
+		ct.dfs[most_sym] = -1;       // st[(1 >> 0) - 1] = st[0] = 1
+		return 1;
+	}
+	u32 dyn_min = ((1u << deflog) * 8) >> 3;
+	if (maxsym <= defmax && (nseq < dyn_min || most < (nseq >> (deflog - 1)))) {  // Predefined_Mode
+		ct.log = deflog;
+		ze_fse_build_ctable(ct, defnorm, defmax, e.tsym, e.cumul);
+		return 0;
+	}
+	u32 log = ze_fse_table_log(maxlog, nseq, maxsym);
+	ze_fse_normalize(e.norm, cnt, nseq, maxsym, log);
+	u32 nc = ze_fse_write_ncount(p, (u32)(end - p), e.norm, maxsym, log);
+	if (!nc) return 0xff;
+	p += nc;
+	ct.log = log;
+	ze_fse_build_ctable(ct, e.norm, maxsym, e.tsym, e.cumul);
+	return 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: match finding over one block.  Returns nseq; *lit_count = literals gathered into S->lit,
+// with the trailing literals (after the last match) included.
+struct ZeRep {
+	u32 r0, r1, r2;
+	u32 known;  // how many of r0,r1,r2 the decoder is known to hold (3 at frame start)
+};
+
+ZG_DEV u32 ze_hash4(u32 v, u32 hlog) { return (v * 2654435761u) >> (32 - hlog); }
+
+ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, ZeRep rep, u32 lazy, u32* lit_count) {
+	u32 lane = zg_lane();
+	u32 hlog = 8;
+	while (hlog < ZE_HLOG_MAX && (1u << hlog) < n) hlog++;
+	u16* htab = W->u.htab;
+	{
+		u32* h32 = (u32*)htab;
+		for (u32 i = lane; i < (1u << hlog) / 2; i += 32) h32[i] = 0;
+		for (u32 i = lane; i < 256; i += 32) W->hist[i] = 0;
+	}
+	__syncwarp();
+	u32 anchor = 0, lpos = 0, nseq = 0, ip = 0;
+	while (ip + ZE_MINMATCH <= n && nseq < ZE_MAXSEQ - 1) {
+		u32 pos = ip + lane;
+		bool valid = pos + 4 <= n;
+		u32 v = valid ? zg_ld32(src + pos) : 0;
+		u32 h = valid ? ze_hash4(v, hlog) : (0x80000000u | lane);
+		u32 te = valid ? htab[h] : 0;
+		u32 peers = __match_any_sync(ZG_FULL, h);
+		__syncwarp();
+		if (valid && (peers >> lane) == 1u) htab[h] = (u16)pos;  // highest lane of each hash group
+		// candidate: nearest earlier lane with the same hash, else the table entry
+		u32 lower = peers & zg_lanemask_lt();
+		i32 cand = -1;
+		if (valid) {
+			if (lower) {
+				cand = (i32)(ip + (31u - (u32)__clz((int)lower)));
+			} else {
+				i32 c = (i32)((pos & ~0xffffu) | te);
+				if (c >= (i32)pos) c -= 65536;
+				cand = c;
+			}
+		}
+		u32 mlen = 0;
+		if (cand >= 0 && zg_ld32(src + cand) == v) {
+			u32 maxl = zg_min<u32>(n - pos, ZE_LANE_CAP);
+			mlen = 4;
+			while (mlen + 4 <= maxl) {
+				u32 x = zg_ld32(src + pos + mlen) ^ zg_ld32(src + cand + mlen);
+				if (x) {
+					mlen += ((u32)__ffs((int)x) - 1) >> 3;
+					break;
+				}
+				mlen += 4;
+			}
+			if (mlen + 4 > maxl)
+				while (mlen < maxl && src[pos + mlen] == src[cand + mlen]) mlen++;
+		}
+		u32 moff = mlen ? pos - (u32)cand : 0;
+		__syncwarp();
+		// ---- warp-uniform parse of this window ----
+		u32 has = __ballot_sync(ZG_FULL, mlen >= ZE_MINMATCH);
+		u32 cur = ip;
+		while (has && nseq < ZE_MAXSEQ - 1) {
+			u32 i = (u32)__ffs((int)has) - 1;
+			u32 L = __shfl_sync(ZG_FULL, mlen, (int)i), O = __shfl_sync(ZG_FULL, moff, (int)i);
+			if (lazy && i < 31 && ((has >> (i + 1)) & 1)) {
+				u32 L1 = __shfl_sync(ZG_FULL, mlen, (int)i + 1);
+				if (L1 > L + 1) {
+					has &= ~(1u << i);
+					continue;
+				}
+			}
+			u32 p = ip + i;
+			if (L >= ZE_LANE_CAP && p + L < n) {
+				// whole-warp extension, 128 bytes per step
+				for (;;) {
+					u32 q = p + L + 4 * lane;
+					u32 eq = 0;
+					if (q + 4 <= n) {
+						u32 x = zg_ld32(src + q) ^ zg_ld32(src + q - O);
+						eq = x ? (((u32)__ffs((int)x) - 1) >> 3) : 4;
+					} else {
+						while (q + eq < n && eq < 4 && src[q + eq] == src[q + eq - O]) eq++;
+					}
+					u32 full = __ballot_sync(ZG_FULL, eq == 4);
+					if (full == ZG_FULL) {
+						L += 128;
+						continue;
+					}
+					u32 first = (u32)__ffs((int)~full) - 1;
+					L += 4 * first + __shfl_sync(ZG_FULL, eq, (int)first);
+					break;
+				}
+			}
+			u32 ll = p - anchor;
+			// literals of this sequence -> S->lit, histogram
+			for (u32 k = lane; k < ll; k += 32) {
+				u32 b = src[anchor + k];
+				S->lit[lpos + k] = (u8)b;
+				atomicAdd(&W->hist[b], 1u);
+			}
+			// repeat-offset codes (RFC 8878 §3.1.1.5), tracking which history slots are known
+			u32 ofb;
+			if (ll > 0) {
+				if (rep.known >= 1 && O == rep.r0) ofb = 1;
+				else if (rep.known >= 2 && O == rep.r1) ofb = 2;
+				else if (rep.known >= 3 && O == rep.r2) ofb = 3;
+				else ofb = O + 3;
+			} else {
+				if (rep.known >= 2 && O == rep.r1) ofb = 1;
+				else if (rep.known >= 3 && O == rep.r2) ofb = 2;
+				else if (rep.known >= 1 && rep.r0 > 1 && O == rep.r0 - 1) ofb = 3;
+				else ofb = O + 3;
+			}
+			if (ofb > 3) {
+				rep.r2 = rep.r1;
+				rep.r1 = rep.r0;
+				rep.r0 = O;
+				if (rep.known < 3) rep.known++;
+			} else {
+				u32 idx = ofb - 1 + (ll == 0 ? 1 : 0);
+				if (idx == 1) {
+					u32 t = rep.r1;
+					rep.r1 = rep.r0;
+					rep.r0 = t;
+				} else if (idx == 2) {
+					u32 t = rep.r2;
+					rep.r2 = rep.r1;
+					rep.r1 = rep.r0;
+					rep.r0 = t;
+				} else if (idx == 3) {
+					rep.r2 = rep.r1;
+					rep.r1 = rep.r0;
+					rep.r0 = O;
+					// r0-1 pushed: slots shift down, still as many known as before (at least 1)
+				}
+			}
+			if (lane == 0) {
+				S->ll[nseq] = ll;
+				S->ml[nseq] = L;
+				S->ofb[nseq] = ofb;
+			}
+			nseq++;
+			lpos += ll;
+			anchor = p + L;
+			cur = anchor;
+			u32 rel = cur - ip;
+			has = rel >= 32 ? 0 : (has & ~((1u << rel) - 1u));
+		}
+		ip = zg_max<u32>(ip + 32, cur);
+	}
+	// trailing literals
+	u32 rest = n - anchor;
+	for (u32 k = lane; k < rest; k += 32) {
+		u32 b = src[anchor + k];
+		S->lit[lpos + k] = (u8)b;
+		atomicAdd(&W->hist[b], 1u);
+	}
+	lpos += rest;
+	__syncwarp();
+	*lit_count = lpos;
+	return nseq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: entropy-code the block into dst[0..cap).  Returns the body size, or 0 if it would not be
+// smaller than the raw block.  All lanes call.
+ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZeScratch* S, u32 nseq, u32 nlit, u8* dst, u32 cap) {
+	ZeEnt& e = W->u.e;
+	u32 lane = zg_lane();
+	if (cap < 16) return 0;
+	u8* end = dst + cap;
+	u8* p = dst;
+	// ---- literals section ----
+	u32 maxc = 0;
+	for (u32 k = 0; k < 8; k++) maxc = zg_max<u32>(maxc, W->hist[k * 32 + lane]);
+	maxc = zg_warp_max(maxc);
+	u32 mode = 0;  // 0 raw, 1 rle, 2 huffman
+	u32 maxbits = 0, maxsym = 0, tree = 0;
+	u32 sbits[4] = {0, 0, 0, 0}, sbytes[4] = {0, 0, 0, 0};
+	u32 streams = nlit < 256 ? 1 : 4;
+	u32 seg = (nlit + 3) >> 2;
+	u32 comp = 0;
+	if (nlit > 1 && maxc == nlit) {
+		mode = 1;
+	} else if (nlit >= 64) {
+		maxbits = ze_huf_build(W, &maxsym);
+		if (maxbits) {
+			if (lane == 0) W->misc[1] = ze_huf_write_tree(W, maxsym);
+			__syncwarp();
+			tree = W->misc[1];
+			__syncwarp();
+		}
+		if (tree) {
+			if (streams == 1) {
+				sbits[0] = ze_huf_count_bits(e, S->lit, nlit);
+				sbytes[0] = (sbits[0] + 8) >> 3;
+				comp = tree + sbytes[0];
+			} else {
+				for (u32 k = 0; k < 4; k++) {
+					u32 m = k < 3 ? seg : nlit - 3 * seg;
+					sbits[k] = ze_huf_count_bits(e, S->lit + k * seg, m);
+					sbytes[k] = (sbits[k] + 8) >> 3;
+				}
+				comp = tree + 6 + sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
+			}
+			if (comp + (nlit >> 6) + 2 < nlit && (streams == 4 || (comp < 1024 && nlit < 1024)) && sbytes[0] < 65536 &&
+			    sbytes[1] < 65536 && sbytes[2] < 65536)
+				mode = 2;
+		}
+	}
+	if (mode == 2) {
+		u32 hdr = (streams == 1 || (comp < 1024 && nlit < 1024)) ? 3 : (comp < 16384 && nlit < 16384) ? 4 : 5;
+		if (p + hdr + comp > end) return 0;
+		if (lane == 0) {
+			if (hdr == 3) {
+				u32 v = 2u | ((streams == 1 ? 0u : 1u) << 2) | (nlit << 4) | (comp << 14);
+				p[0] = (u8)v;
+				p[1] = (u8)(v >> 8);
+				p[2] = (u8)(v >> 16);
+			} else if (hdr == 4) {
+				u32 v = 2u | (2u << 2) | (nlit << 4) | (comp << 18);
+				p[0] = (u8)v;
+				p[1] = (u8)(v >> 8);
+				p[2] = (u8)(v >> 16);
+				p[3] = (u8)(v >> 24);
+			} else {
+				u64 v = 2u | (3u << 2) | ((u64)nlit << 4) | ((u64)comp << 22);
+				for (u32 i = 0; i < 5; i++) p[i] = (u8)(v >> (8 * i));
+			}
+		}
+		p += hdr;
+		for (u32 i = lane; i < tree; i += 32) p[i] = e.wdesc[i];
+		p += tree;
+		if (streams == 1) {
+			ze_huf_encode_stream(W, S->lit, nlit, p, sbits[0]);
+			p += sbytes[0];
+		} else {
+			if (lane == 0) {
+				p[0] = (u8)sbytes[0];
+				p[1] = (u8)(sbytes[0] >> 8);
+				p[2] = (u8)sbytes[1];
+				p[3] = (u8)(sbytes[1] >> 8);
+				p[4] = (u8)sbytes[2];
+				p[5] = (u8)(sbytes[2] >> 8);
+			}
+			p += 6;
+			for (u32 k = 0; k < 4; k++) {
+				u32 m = k < 3 ? seg : nlit - 3 * seg;
+				ze_huf_encode_stream(W, S->lit + k * seg, m, p, sbits[k]);
+				p += sbytes[k];
+			}
+		}
+	} else {
+		u32 payload = mode == 1 ? 1 : nlit;
+		u32 hdr = nlit < 32 ? 1 : nlit < 4096 ? 2 : 3;
+		if (p + hdr + payload > end) return 0;
+		if (lane == 0) {
+			if (hdr == 1) p[0] = (u8)(mode | (nlit << 3));
+			else if (hdr == 2) {
+				u32 v = mode | (1u << 2) | (nlit << 4);
+				p[0] = (u8)v;
+				p[1] = (u8)(v >> 8);
+			} else {
+				u32 v = mode | (3u << 2) | (nlit << 4);
+				p[0] = (u8)v;
+				p[1] = (u8)(v >> 8);
+				p[2] = (u8)(v >> 16);
+			}
+		}
+		p += hdr;
+		if (mode == 1) {
+			if (lane == 0) p[0] = S->lit[0];
+		} else {
+			for (u32 i = lane; i < nlit; i += 32) p[i] = S->lit[i];
+		}
+		p += payload;
+	}
+	__syncwarp();
+	// ---- sequences section ----
+	if (p + 4 > end) return 0;
+	if (nseq == 0) {
+		if (lane == 0) *p = 0;
+		p++;
+		return (u32)(p - dst);
+	}
+	if (lane == 0) {
+		if (nseq < 128) p[0] = (u8)nseq;
+		else if (nseq < 0x7F00) {
+			p[0] = (u8)((nseq >> 8) + 128);
+			p[1] = (u8)nseq;
+		} else {
+			p[0] = 255;
+			p[1] = (u8)(nseq - 0x7F00);
+			p[2] = (u8)((nseq - 0x7F00) >> 8);
+		}
+	}
+	p += nseq < 128 ? 1 : nseq < 0x7F00 ? 2 : 3;
+	// codes + histograms
+	for (u32 i = lane; i < 3 * 64; i += 32) (&e.hist3[0][0])[i] = 0;
+	__syncwarp();
+	u32 mx_ll = 0, mx_ml = 0, mx_of = 0;
+	for (u32 i = lane; i < nseq; i += 32) {
+		u32 lc = ze_ll_code(S->ll[i]), mc = ze_ml_code(S->ml[i] - 3), oc = zs_highbit(S->ofb[i]);
+		S->codes[i] = lc | (mc << 8) | (oc << 16);
+		atomicAdd(&e.hist3[0][lc], 1u);
+		atomicAdd(&e.hist3[1][mc], 1u);
+		atomicAdd(&e.hist3[2][oc], 1u);
+		mx_ll = zg_max<u32>(mx_ll, lc);
+		mx_ml = zg_max<u32>(mx_ml, mc);
+		mx_of = zg_max<u32>(mx_of, oc);
+	}
+	mx_ll = zg_warp_max(mx_ll);
+	mx_ml = zg_warp_max(mx_ml);
+	mx_of = zg_warp_max(mx_of);
+	__syncwarp();
+	if (lane == 0) {
+		bool ok = true;
+		u8* q = p + 1;  // after the modes byte
+		ZeCT ct_ll, ct_ml, ct_of;
+		u32 m_ll = ze_seq_table(e, 0, e.hist3[0], nseq, mx_ll, ZS_LL_MAXLOG, 6, ZS_LL_DEFAULT_NORM, 35, q, end, ct_ll);
+		u32 m_of = m_ll == 0xff ? 0xff : ze_seq_table(e, 2, e.hist3[2], nseq, mx_of, ZS_OF_MAXLOG, 5, ZS_OF_DEFAULT_NORM, 28, q, end, ct_of);
+		u32 m_ml = m_of == 0xff ? 0xff : ze_seq_table(e, 1, e.hist3[1], nseq, mx_ml, ZS_ML_MAXLOG, 6, ZS_ML_DEFAULT_NORM, 52, q, end, ct_ml);
+		if (m_ll == 0xff || m_of == 0xff || m_ml == 0xff) ok = false;
+		if (ok) {
+			*p = (u8)((m_ll << 6) | (m_of << 4) | (m_ml << 2));
+			ZeBitW bw;
+			ze_bw_init(bw, q, end);
+			// libzstd ZSTD_encodeSequences order (mirror of the decoder)
+			u32 i = nseq - 1;
+			u32 c = S->codes[i];
+			u32 lc = c & 0xff, mc = (c >> 8) & 0xff, oc = c >> 16;
+			u32 s_ml = ze_fse_init_state(ct_ml, mc), s_of = ze_fse_init_state(ct_of, oc), s_ll = ze_fse_init_state(ct_ll, lc);
+			ze_bw_add(bw, S->ll[i] - ZS_LL_BASE[lc], ZS_LL_BITS[lc]);
+			ze_bw_add(bw, S->ml[i] - ZS_ML_BASE[mc], ZS_ML_BITS[mc]);
+			ze_bw_add(bw, S->ofb[i] - (1u << oc), oc);
+			while (i > 0) {
+				i--;
+				c = S->codes[i];
+				lc = c & 0xff;
+				mc = (c >> 8) & 0xff;
+				oc = c >> 16;
+				ze_fse_encode(bw, ct_of, s_of, oc);
+				ze_fse_encode(bw, ct_ml, s_ml, mc);
+				ze_fse_encode(bw, ct_ll, s_ll, lc);
+				ze_bw_add(bw, S->ll[i] - ZS_LL_BASE[lc], ZS_LL_BITS[lc]);
+				ze_bw_add(bw, S->ml[i] - ZS_ML_BASE[mc], ZS_ML_BITS[mc]);
+				ze_bw_add(bw, S->ofb[i] - (1u << oc), oc);
+			}
+			ze_fse_flush_state(bw, ct_ml, s_ml);
+			ze_fse_flush_state(bw, ct_of, s_of);
+			ze_fse_flush_state(bw, ct_ll, s_ll);
+			u8* endp = ze_bw_close(bw);
+			ok = !bw.ovf;
+			W->misc[2] = (u32)(endp - dst);
+		}
+		W->misc[1] = ok ? 1 : 0;
+	}
+	__syncwarp();
+	u32 ok = W->misc[1], total = W->misc[2];
+	__syncwarp();
+	return ok ? total : 0;
+}
+
+struct ZeParams {
+	u32 lazy;      // 1: one-step lazy parse (levels >= 3)
+	u32 window;    // reserved
+};
+
+__global__ void __launch_bounds__(ZE_WARPS * 32)
+k_zstd_encode_blocks(const u8* __restrict__ blob, const u64* __restrict__ file_off, const u64* __restrict__ comp_off,
+                     const u64* __restrict__ file_len,
+                     const u32* __restrict__ ulist, const u64* __restrict__ blk_base, u32 nuniq, u64 nblocks, u8* comp,
+                     u32* __restrict__ blk_csize, ZeScratch* scratch, u32* queue, ZeParams prm) {
+	ZG_DYN_SMEM(ZeWarp, sm);
+	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	ZeWarp* W = &sm[warp];
+	ZeScratch* S = scratch + (size_t)(blockIdx.x * ZE_WARPS + warp);
+	for (;;) {
+		u32 b = 0;
+		if (lane == 0) b = atomicAdd(queue, 1u);
+		b = __shfl_sync(ZG_FULL, b, 0);
+		if (b >= nblocks) break;
+		// block -> (unique file, block index): last u with blk_base[u] <= b
+		u32 lo = 0, hi = nuniq - 1;
+		while (lo < hi) {
+			u32 mid = (lo + hi + 1) >> 1;
+			if (blk_base[mid] <= b) lo = mid;
+			else hi = mid - 1;
+		}
+		u32 f = ulist[lo];
+		u64 j = b - blk_base[lo];
+		u64 flen = file_len[f];
+		u64 boff = j * ZS_BLOCK_MAX;
+		u32 n = (u32)zg_min<u64>(ZS_BLOCK_MAX, flen - zg_min<u64>(flen, boff));
+		const u8* src = blob + file_off[f] + boff;
+		u8* dst = comp + comp_off[f] + boff;
+		u32 csize = 0;
+		if (n >= 16) {
+			ZeRep rep;
+			rep.r0 = 1;
+			rep.r1 = 4;
+			rep.r2 = 8;
+			rep.known = j == 0 ? 3 : 0;  // later blocks are encoded independently of their predecessors
+			u32 nlit = 0;
+			u32 nseq = ze_match_block(W, S, src, n, rep, prm.lazy, &nlit);
+			__syncwarp();
+			csize = ze_entropy_block(W, S, nseq, nlit, dst, n - 1);
+		}
+		__syncwarp();
+		if (lane == 0) blk_csize[b] = csize ? csize : (ZE_RAW | n);
+	}
+}
+
+size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
+                          const u32* ulist,
+                          const u64* blk_base, u32 nuniq, u64 nblocks, u8* comp, u32* blk_csize, int level) {
+	if (nblocks == 0) return 0;
+	u32 grid = (u32)zg_min<u64>((nblocks + ZE_WARPS - 1) / ZE_WARPS, (u64)zg_sm_count() * 3);
+	if (w.scratch.reserve((size_t)grid * ZE_WARPS * sizeof(ZeScratch)) || w.queue.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
+	cudaMemsetAsync(w.queue.p, 0, 16, s);
+	ZeParams prm;
+	prm.lazy = level >= 3 ? 1 : 0;
+	prm.window = 0;
+	size_t smem = sizeof(ZeWarp) * ZE_WARPS;
+	static bool attr_set = false;
+	if (!attr_set) {
+		if (cudaFuncSetAttribute(k_zstd_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+			return ZG_ERR(ZG_error_device);
+		attr_set = true;
+	}
+	ZG_LAUNCH(k_zstd_encode_blocks, grid, ZE_WARPS * 32, smem, s, blob, file_off, comp_off, file_len, ulist, blk_base, nuniq, nblocks, comp,
+	          blk_csize, w.scratch.as<ZeScratch>(), w.queue.as<u32>(), prm);
+	ZG_COUNT_LAUNCH();
+	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
+}
