@@ -172,8 +172,16 @@ size_t zg_corpus_generate_dev(void* cuda_stream, uint8_t* out, const uint64_t* s
 size_t zg_corpus_generate_host(uint8_t* out, const uint64_t* seg_off, const uint32_t* seg_len,
                                const uint8_t* seg_kind, const uint64_t* seg_key, uint64_t n_segments);
 
+/* first[i] = 1 iff digests[i] does not occur at a smaller index; rep[i] = that smallest index.
+ * Device pointers.  (content_frame.rs:30 over an ordered digest list gathered from several GPUs.) */
+size_t zg_dedup_dev(void* cuda_stream, const uint8_t* digests, uint64_t n, uint8_t* first, uint64_t* rep);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t zg_kernel_launch_count(void);
+/* optional per-kernel device timing (CUDA events on the launching stream) for roofline reports.
+ * k: 0 BLAKE3, 1 Zstd encode, 2 Zstd decode, 3 frame assemble, 4 XXH64, 5 dedup */
+void zg_profile_enable(int on);
+size_t zg_profile_read(int k, double* total_ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

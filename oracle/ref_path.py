@@ -119,10 +119,11 @@ class RefEncoder:
     def compress_frame(self, content: bytes) -> bytes:  # lowlevel_frames.rs:19-39
         n = len(content)
         cap = n + max(1024, n // 10)
-        dst = ctypes.create_string_buffer(cap)
-        src = (ctypes.c_char * n).from_buffer_copy(content) if n else None
-        r = _check(_zstd.ZSTD_compress2(self.cctx, dst, cap, src, n))
-        return dst.raw[:r]
+        if cap > getattr(self, "_dst_cap", 0):  # one reusable destination (the Rust side allocates a Vec per frame)
+            self._dst = ctypes.create_string_buffer(cap)
+            self._dst_cap = cap
+        r = _check(_zstd.ZSTD_compress2(self.cctx, self._dst, cap, bytes(content) if n else None, n))
+        return ctypes.string_at(self._dst, r)
 
     def add_data_frame(self, content: bytes) -> bytes:  # content_frame.rs:20-60
         offset = self.offset
@@ -155,17 +156,22 @@ def ref_decompress_stream(archive: bytes, offset: int) -> bytes:
         pos = offset
         chunks = []
         done = False
+        base = ctypes.cast(ctypes.c_char_p(archive), _vp).value if isinstance(archive, bytes) else None
+        outmem = ctypes.create_string_buffer(out_size)
+        out_addr = ctypes.cast(outmem, _vp)
         while not done:
-            gulp = archive[pos : pos + in_size]
-            if not gulp:
+            avail = min(in_size, len(archive) - pos)
+            if avail <= 0:
                 raise ZstdError("unexpected end of archive")
-            inbuf_mem = ctypes.create_string_buffer(bytes(gulp), len(gulp))
-            inbuf = _Buf(ctypes.cast(inbuf_mem, _vp), len(gulp), 0)
+            if base is not None:  # read straight from the archive bytes (the reference reads into a fresh 131 075-byte Vec)
+                inbuf = _Buf(base + pos, avail, 0)
+            else:
+                inbuf_mem = ctypes.create_string_buffer(bytes(archive[pos : pos + avail]), avail)
+                inbuf = _Buf(ctypes.cast(inbuf_mem, _vp), avail, 0)
             while True:
-                outmem = ctypes.create_string_buffer(out_size)
-                outbuf = _Buf(ctypes.cast(outmem, _vp), out_size, 0)
+                outbuf = _Buf(out_addr, out_size, 0)
                 hint = _check(_zstd.ZSTD_decompressStream(dctx, ctypes.byref(outbuf), ctypes.byref(inbuf)))
-                chunks.append(outmem.raw[: outbuf.pos])
+                chunks.append(ctypes.string_at(out_addr, outbuf.pos))
                 if hint == 0:
                     done = True
                     break

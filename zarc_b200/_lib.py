@@ -63,6 +63,11 @@ SIGNATURES = {
     "zg_corpus_generate_dev": (_sz, [_vp, _vp, _vp, _vp, _vp, _vp, _u64]),
     "zg_corpus_generate_host": (_sz, [_vp, _vp, _vp, _vp, _vp, _u64]),
     "zg_kernel_launch_count": (_u64, []),
+    "zg_dedup_dev": (_sz, [_vp, _vp, _u64, _vp, _vp]),
+    "zg_profile_enable": (None, [C.c_int]),
+    "zg_profile_read": (_sz, [C.c_int, C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "zg_alloc_pinned": (_vp, [_sz]),
+    "zg_free_pinned": (None, [_vp]),
 }
 
 # libzstd's ZSTD_cParameter numbers (crates/zarc-cli/src/pack.rs:140-195 maps --zstd names to these)

@@ -520,3 +520,44 @@ size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* inp
 }  // extern "C"
 
 // the compression context and zg_pack_batch live in abi_pack.cu
+
+// ---------------------------------------------------------------------------------------------
+// per-kernel device timing for bench.py's roofline: cudaEvent pairs on the launching stream
+#include <utility>
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof[ZG_K_COUNT];
+static cudaEvent_t g_prof_open[ZG_K_COUNT];
+void zg_prof_begin(int k, cudaStream_t s) {
+	if (!g_prof_on) return;
+	cudaEvent_t a;
+	cudaEventCreate(&a);
+	cudaEventRecord(a, s);
+	g_prof_open[k] = a;
+}
+void zg_prof_end(int k, cudaStream_t s) {
+	if (!g_prof_on) return;
+	cudaEvent_t b;
+	cudaEventCreate(&b);
+	cudaEventRecord(b, s);
+	g_prof[k].push_back({g_prof_open[k], b});
+}
+extern "C" {
+void zg_profile_enable(int on) { g_prof_on = on != 0; }
+// total device milliseconds and launch count of kernel class k since the last read
+size_t zg_profile_read(int k, double* ms, uint64_t* launches) {
+	if (k < 0 || k >= ZG_K_COUNT) return ZG_ERR(ZG_error_parameter_outOfBound);
+	double t = 0;
+	for (auto& pr : g_prof[k]) {
+		cudaEventSynchronize(pr.second);
+		float f = 0;
+		cudaEventElapsedTime(&f, pr.first, pr.second);
+		t += f;
+		cudaEventDestroy(pr.first);
+		cudaEventDestroy(pr.second);
+	}
+	if (ms) *ms = t;
+	if (launches) *launches = g_prof[k].size();
+	g_prof[k].clear();
+	return 0;
+}
+}

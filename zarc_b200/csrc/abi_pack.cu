@@ -358,3 +358,27 @@ size_t zg_compress2(zg_cctx* c, void* dst, size_t cap, const void* src, size_t n
 }
 
 }  // extern "C"
+
+// First-occurrence decisions over an ordered list of digests (content_frame.rs:30), on the device.
+// Used when digests from several GPUs are gathered into global file order.
+extern "C" size_t zg_dedup_dev(void* stream, const uint8_t* digests, uint64_t n, uint8_t* first, uint64_t* rep) {
+	ZG_NEED_DEVICE();
+	if (n == 0) return 0;
+	cudaStream_t s = (cudaStream_t)stream;
+	u64 want = 1024;
+	while (want < 2 * n) want <<= 1;
+	ZgBuf table, tmp;
+	size_t r = 0;
+	if (table.reserve(want * 4) || tmp.reserve(n * 8 * 4)) r = ZG_ERR(ZG_error_memory_allocation);
+	if (!r) {
+		cudaMemsetAsync(table.p, 0, want * 4, s);
+		cudaMemsetAsync(tmp.p, 0, n * 8 * 4, s);
+		u64* t = tmp.as<u64>();
+		r = zg_pk_dedup_insert(s, digests, 0, n, table.as<u32>(), (u32)want - 1);
+		if (!r) r = zg_pk_dedup_resolve(s, digests, 0, n, table.as<u32>(), (u32)want - 1, t, rep, first, t + n, t + 2 * n, t + 3 * n);
+		if (cudaStreamSynchronize(s) != cudaSuccess) r = ZG_ERR(ZG_error_device);
+	}
+	table.release();
+	tmp.release();
+	return r;
+}

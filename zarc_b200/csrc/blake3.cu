@@ -130,7 +130,9 @@ size_t zg_blake3_run(cudaStream_t s, ZgB3Work& w, const u8* blob, const u64* off
 	cudaMemsetAsync(w.ctr.p, 0, 16, s);
 	u64 warps_needed = n;
 	u32 grid = (u32)zg_min<u64>((warps_needed + B3_WARPS - 1) / B3_WARPS, (u64)zg_sm_count() * 8);
+	zg_prof_begin(ZG_K_BLAKE3, s);
 	ZG_LAUNCH(k_blake3_files, grid, B3_WARPS * 32, 0, s, blob, off, len, n, digests, w.big.as<u64>(), w.ctr.as<u32>());
+	zg_prof_end(ZG_K_BLAKE3, s);
 	ZG_COUNT_LAUNCH();
 	u32* hcount = w.h.as<u32>();
 	cudaMemcpyAsync(hcount, w.ctr.p, 4, cudaMemcpyDeviceToHost, s);

@@ -97,3 +97,8 @@ struct ZgZeWork {
 size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
                           const u32* ulist,
                           const u64* blk_base, u32 nuniq, u64 nblocks, u8* comp, u32* blk_csize, int level);
+
+// ---- per-kernel device timing (abi.cu): CUDA events on the launching stream, off by default ----
+enum { ZG_K_BLAKE3 = 0, ZG_K_ENCODE = 1, ZG_K_DECODE = 2, ZG_K_ASSEMBLE = 3, ZG_K_XXH64 = 4, ZG_K_DEDUP = 5, ZG_K_COUNT = 6 };
+void zg_prof_begin(int k, cudaStream_t s);
+void zg_prof_end(int k, cudaStream_t s);

@@ -643,8 +643,10 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 	u32 grid = (u32)zg_min<u64>((n + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * 5);
 	if (w.lit.reserve((size_t)grid * ZD_WARPS * ZD_LITBUF) || w.queue.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.queue.p, 0, 16, s);
+	zg_prof_begin(ZG_K_DECODE, s);
 	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, 0, s, archive, archive_len, off, len, ulen, out_off, n, out, out_cap,
 	          w.lit.as<u8>(), w.queue.as<u32>(), status, produced, cksums);
+	zg_prof_end(ZG_K_DECODE, s);
 	ZG_COUNT_LAUNCH();
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
 }

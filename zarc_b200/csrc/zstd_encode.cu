@@ -948,8 +948,10 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 			return ZG_ERR(ZG_error_device);
 		attr_set = true;
 	}
+	zg_prof_begin(ZG_K_ENCODE, s);
 	ZG_LAUNCH(k_zstd_encode_blocks, grid, ZE_WARPS * 32, smem, s, blob, file_off, comp_off, file_len, ulist, blk_base, nuniq, nblocks, comp,
 	          blk_csize, w.scratch.as<ZeScratch>(), w.queue.as<u32>(), prm);
+	zg_prof_end(ZG_K_ENCODE, s);
 	ZG_COUNT_LAUNCH();
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
 }
