@@ -485,22 +485,63 @@ ZG_DEV u32 zd_compressed_block(ZdWarp* W, ZdState& st, const u8* src, u32 n, u8*
 			}
 			if (!__all_sync(ZG_FULL, ok)) return ZS_E_CORRUPT;
 			__syncwarp();  // lane 0's batch in shared memory is visible to the warp
-			// execute the batch
-			for (u32 k = 0; k < cnt; k++) {
-				u32 ll = W->seq_ll[k], ml = W->seq_ml[k], of = W->seq_of[k];
-				if (lpos + ll > regen) return ZS_E_CORRUPT;
-				if (o + ll + ml > cap) return ZS_E_DST_SMALL;
-				if ((u64)of > o + ll) return ZS_E_CORRUPT;
-				u8* d = out + o;
-				if (ll) {
-					if (lit_rle) zg_warp_fill(d, rle_byte, ll);
-					else zg_warp_copy(d, lit + lpos, ll);
+			// execute the batch: one sequence per lane.  Output and literal positions come from warp
+			// scans; (a) all literal runs and (b) all matches whose source lies wholly before this
+			// batch's output are independent and copied lane-parallel; (c) the remaining matches
+			// (sources inside the batch, incl. overlapping ones) go in order, warp-cooperatively.
+			{
+				bool act = lane < cnt;
+				u32 ll = act ? W->seq_ll[lane] : 0, ml = act ? W->seq_ml[lane] : 0, of = act ? W->seq_of[lane] : 0;
+				u32 incl = zg_warp_incl_scan(ll + ml), lincl = zg_warp_incl_scan(ll);
+				u32 btot = __shfl_sync(ZG_FULL, incl, 31), ltot = __shfl_sync(ZG_FULL, lincl, 31);
+				if (lpos + ltot > regen) return ZS_E_CORRUPT;
+				if (o + btot > cap) return ZS_E_DST_SMALL;
+				u64 mstart = o + (incl - ll - ml) + ll;  // where my match begins in the frame output
+				if (__any_sync(ZG_FULL, act && (u64)of > mstart)) return ZS_E_CORRUPT;
+				u8* d = out + mstart - ll;
+				u32 lsrc = lpos + (lincl - ll);
+				// (a) literals
+				u32 longl = __ballot_sync(ZG_FULL, ll >= 48);
+				if (ll < 48) {
+					if (lit_rle) for (u32 k = 0; k < ll; k++) d[k] = (u8)rle_byte;
+					else for (u32 k = 0; k < ll; k++) d[k] = lit[lsrc + k];
+				}
+				while (longl) {
+					int l = __ffs((int)longl) - 1;
+					longl &= longl - 1;
+					u32 n2 = __shfl_sync(ZG_FULL, ll, l), s2 = __shfl_sync(ZG_FULL, lsrc, l);
+					u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)d, l);
+					if (lit_rle) zg_warp_fill((u8*)(uintptr_t)d2, rle_byte, n2);
+					else zg_warp_copy((u8*)(uintptr_t)d2, lit + s2, n2);
+				}
+				// (b) independent matches
+				u8* md = out + mstart;
+				bool indep = act && ml > 0 && mstart - of + ml <= o;
+				u32 longm = __ballot_sync(ZG_FULL, indep && ml >= 48);
+				if (indep && ml < 48) {
+					const u8* ms = md - of;
+					for (u32 k = 0; k < ml; k++) md[k] = ms[k];
+				}
+				while (longm) {
+					int l = __ffs((int)longm) - 1;
+					longm &= longm - 1;
+					u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
+					u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
+					zg_warp_copy((u8*)(uintptr_t)d2, (const u8*)(uintptr_t)d2 - o2, n2);
+				}
+				__syncwarp();
+				// (c) dependent matches, in sequence order
+				u32 dep = __ballot_sync(ZG_FULL, act && ml > 0 && !indep);
+				while (dep) {
+					int l = __ffs((int)dep) - 1;
+					dep &= dep - 1;
+					u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
+					u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
+					zd_warp_match((u8*)(uintptr_t)d2, o2, n2);
 					__syncwarp();
 				}
-				zd_warp_match(d + ll, of, ml);
-				__syncwarp();
-				o += ll + ml;
-				lpos += ll;
+				o += btot;
+				lpos += ltot;
 			}
 			__syncwarp();
 		}

@@ -35,6 +35,7 @@ struct ZeScratch {
 	u32 ml[ZE_MAXSEQ];
 	u32 ofb[ZE_MAXSEQ];   // offBase: 1..3 repeat codes, else offset + 3
 	u32 codes[ZE_MAXSEQ]; // ll | ml << 8 | of << 16
+	u16 stb[3][ZE_MAXSEQ]; // per sequence, per table (LL, ML, OF): FSE state bits value | nbBits << 12
 	u8 lit[ZS_BLOCK_MAX + 64];
 };
 
@@ -474,6 +475,79 @@ ZG_DEV void ze_huf_encode_stream(ZeWarp* W, const u8* lit, u32 m, u8* dst, u32 t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-parallel bit packer: each call, every lane contributes one bit field (<= 96 bits, lane order
+// = stream order, low bits first); fields are placed by a warp scan and OR-ed into a shared window
+// (96 words), whole bytes are flushed to dst, the partial byte carries over.  All lanes call.
+struct ZePack {
+	u32* win;
+	u8* dst;
+	u32 cap;
+	u32 flushed;  // bytes written
+	u32 pend;     // bits pending in the window (< 8 between calls)
+	bool ovf;
+};
+ZG_DEV void ze_pack_init(ZePack& P, u32* win, u8* dst, u32 cap) {
+	P.win = win;
+	P.dst = dst;
+	P.cap = cap;
+	P.flushed = 0;
+	P.pend = 0;
+	P.ovf = false;
+	for (u32 i = zg_lane(); i < 96; i += 32) win[i] = 0;
+	__syncwarp();
+}
+ZG_DEV void ze_pack_chunk(ZePack& P, u64 lo, u32 hi, u32 nb) {
+	u32 lane = zg_lane();
+	u32 incl = zg_warp_incl_scan(nb);
+	u32 chunk_bits = __shfl_sync(ZG_FULL, incl, 31);
+	if (nb) {
+		u32 start = P.pend + incl - nb;
+		u32 wi = start >> 5, sh = start & 31;
+		u64 a = lo << sh;
+		u32 w0 = (u32)a, w1 = (u32)(a >> 32);
+		u32 w2 = sh ? (u32)(lo >> (64 - sh)) : 0;
+		u32 w3 = 0;
+		if (nb > 64) {  // bits 64.. of the field
+			u64 b = (u64)hi << sh;
+			w2 |= (u32)b;
+			w3 = (u32)(b >> 32);
+		}
+		if (w0) atomicOr(&P.win[wi], w0);
+		if (w1) atomicOr(&P.win[wi + 1], w1);
+		if (w2) atomicOr(&P.win[wi + 2], w2);
+		if (w3) atomicOr(&P.win[wi + 3], w3);
+	}
+	__syncwarp();
+	u32 total = P.pend + chunk_bits;
+	u32 nbytes = total >> 3;
+	if (P.flushed + nbytes > P.cap) {
+		P.ovf = true;
+		nbytes = 0;  // stop writing; the caller discards the block
+	}
+	for (u32 i = lane; i < nbytes; i += 32) P.dst[P.flushed + i] = (u8)(P.win[i >> 2] >> (8 * (i & 3)));
+	u32 keep = (total & 7) ? ((P.win[(total >> 3) >> 2] >> (8 * ((total >> 3) & 3))) & 0xffu) : 0u;
+	__syncwarp();
+	u32 nwords = (total + 31) >> 5;
+	for (u32 i = lane; i <= nwords && i < 96; i += 32) P.win[i] = 0;
+	__syncwarp();
+	if (lane == 0) P.win[0] = keep;
+	__syncwarp();
+	P.flushed += nbytes;
+	P.pend = total & 7;
+}
+// flush the last partial byte; returns total bytes
+ZG_DEV u32 ze_pack_finish(ZePack& P) {
+	if (P.pend) {
+		if (P.flushed + 1 > P.cap) P.ovf = true;
+		else if (zg_lane() == 0) P.dst[P.flushed] = (u8)P.win[0];
+		P.flushed += 1;
+		P.pend = 0;
+	}
+	__syncwarp();
+	return P.flushed;
+}
+
+// ---------------------------------------------------------------------------------------------
 // sequence tables: mode choice (libzstd's heuristic for fast strategies), description, CTable.
 // Single lane.  Writes the description at *pp (bounded by end).  Returns mode, or 0xff on overflow.
 ZG_DEV u32 ze_seq_table(ZeEnt& e, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u32 maxlog, u32 deflog, const i16* defnorm,
@@ -841,44 +915,84 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZeScratch* S, u32 nseq, u32 nlit, u8* dst
 		u32 m_of = m_ll == 0xff ? 0xff : ze_seq_table(e, 2, e.hist3[2], nseq, mx_of, ZS_OF_MAXLOG, 5, ZS_OF_DEFAULT_NORM, 28, q, end, ct_of);
 		u32 m_ml = m_of == 0xff ? 0xff : ze_seq_table(e, 1, e.hist3[1], nseq, mx_ml, ZS_ML_MAXLOG, 6, ZS_ML_DEFAULT_NORM, 52, q, end, ct_ml);
 		if (m_ll == 0xff || m_of == 0xff || m_ml == 0xff) ok = false;
-		if (ok) {
-			*p = (u8)((m_ll << 6) | (m_of << 4) | (m_ml << 2));
-			ZeBitW bw;
-			ze_bw_init(bw, q, end);
-			// libzstd ZSTD_encodeSequences order (mirror of the decoder)
-			u32 i = nseq - 1;
-			u32 c = S->codes[i];
-			u32 lc = c & 0xff, mc = (c >> 8) & 0xff, oc = c >> 16;
-			u32 s_ml = ze_fse_init_state(ct_ml, mc), s_of = ze_fse_init_state(ct_of, oc), s_ll = ze_fse_init_state(ct_ll, lc);
-			ze_bw_add(bw, S->ll[i] - ZS_LL_BASE[lc], ZS_LL_BITS[lc]);
-			ze_bw_add(bw, S->ml[i] - ZS_ML_BASE[mc], ZS_ML_BITS[mc]);
-			ze_bw_add(bw, S->ofb[i] - (1u << oc), oc);
-			while (i > 0) {
-				i--;
-				c = S->codes[i];
-				lc = c & 0xff;
-				mc = (c >> 8) & 0xff;
-				oc = c >> 16;
-				ze_fse_encode(bw, ct_of, s_of, oc);
-				ze_fse_encode(bw, ct_ml, s_ml, mc);
-				ze_fse_encode(bw, ct_ll, s_ll, lc);
-				ze_bw_add(bw, S->ll[i] - ZS_LL_BASE[lc], ZS_LL_BITS[lc]);
-				ze_bw_add(bw, S->ml[i] - ZS_ML_BASE[mc], ZS_ML_BITS[mc]);
-				ze_bw_add(bw, S->ofb[i] - (1u << oc), oc);
-			}
-			ze_fse_flush_state(bw, ct_ml, s_ml);
-			ze_fse_flush_state(bw, ct_of, s_of);
-			ze_fse_flush_state(bw, ct_ll, s_ll);
-			u8* endp = ze_bw_close(bw);
-			ok = !bw.ovf;
-			W->misc[2] = (u32)(endp - dst);
-		}
+		if (ok) *p = (u8)((m_ll << 6) | (m_of << 4) | (m_ml << 2));
 		W->misc[1] = ok ? 1 : 0;
+		W->misc[2] = (u32)(q - dst);
+		W->misc[4] = ct_ll.log;
+		W->misc[5] = ct_ml.log;
+		W->misc[6] = ct_of.log;
 	}
 	__syncwarp();
-	u32 ok = W->misc[1], total = W->misc[2];
+	if (!W->misc[1]) return 0;
+	u32 bs_off = W->misc[2];
+	u32 logs[3] = {W->misc[4], W->misc[5], W->misc[6]};
 	__syncwarp();
-	return ok ? total : 0;
+	// Phase 1: the three FSE state chains are independent of each other -> lanes 0,1,2 walk one
+	// each (last sequence first, libzstd's ZSTD_encodeSequences order), leaving per sequence the
+	// bits that chain emits (value | nbBits << 12).
+	if (lane < 3) {
+		u32 t = lane, sh = 8 * lane;  // codes = ll | ml << 8 | of << 16; table index 0 LL, 1 ML, 2 OF
+		ZeCT ct{e.st[t], e.dnb[t], e.dfs[t], logs[t]};
+		u16* out = S->stb[t];
+		u32 state = ze_fse_init_state(ct, (S->codes[nseq - 1] >> sh) & 0xff);
+		out[nseq - 1] = 0;
+		for (u32 i = nseq - 1; i-- > 0;) {
+			u32 code = (S->codes[i] >> sh) & 0xff;
+			u32 nb = (state + ct.dnb[code]) >> 16;
+			out[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+			state = ct.st[(state >> nb) + ct.dfs[code]];
+		}
+		W->misc[8 + t] = state & ((1u << logs[t]) - 1u);
+	}
+	__syncwarp();
+	// Phase 2: every lane assembles one sequence's bit field (<= 89 bits: OF,ML,LL state bits then
+	// LL,ML,OF extra bits), a warp scan places it, and the fields are OR-ed into a shared window.
+	ZePack pk;
+	ze_pack_init(pk, e.window, dst + bs_off, cap - bs_off);
+	for (u32 hi = nseq; hi > 0; hi -= zg_min<u32>(hi, 32u)) {
+		u64 lo64 = 0;
+		u32 hi32 = 0, nb = 0;
+		if (lane < hi) {
+			u32 i = hi - 1 - lane;
+			u32 c = S->codes[i];
+			u32 lc = c & 0xff, mc = (c >> 8) & 0xff, oc = c >> 16;
+			u32 a = S->stb[2][i], b = S->stb[1][i], d = S->stb[0][i];
+			lo64 = a & 0xfff;
+			nb = a >> 12;
+			lo64 |= (u64)(b & 0xfff) << nb;
+			nb += b >> 12;
+			lo64 |= (u64)(d & 0xfff) << nb;
+			nb += d >> 12;
+			lo64 |= (u64)(S->ll[i] - ZS_LL_BASE[lc]) << nb;
+			nb += ZS_LL_BITS[lc];
+			lo64 |= (u64)(S->ml[i] - ZS_ML_BASE[mc]) << nb;
+			nb += ZS_ML_BITS[mc];  // <= 58 bits so far
+			u64 ox = S->ofb[i] - (1u << oc);
+			lo64 |= ox << nb;
+			if (nb + oc > 64) hi32 = (u32)(ox >> (64 - nb));
+			nb += oc;
+		}
+		ze_pack_chunk(pk, lo64, hi32, nb);
+	}
+	{
+		// final states ML, OF, LL then the end marker (lane 0 only contributes)
+		u64 lo64 = 0;
+		u32 nb = 0;
+		if (lane == 0) {
+			lo64 = W->misc[9];
+			nb = logs[1];
+			lo64 |= (u64)W->misc[10] << nb;
+			nb += logs[2];
+			lo64 |= (u64)W->misc[8] << nb;
+			nb += logs[0];
+			lo64 |= (u64)1 << nb;
+			nb += 1;
+		}
+		ze_pack_chunk(pk, lo64, 0, nb);
+	}
+	u32 bytes = ze_pack_finish(pk);
+	__syncwarp();
+	return pk.ovf ? 0 : bs_off + bytes;
 }
 
 struct ZeParams {
