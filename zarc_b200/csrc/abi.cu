@@ -308,6 +308,9 @@ void zg_dctx_free(zg_dctx* d) {
 	if (!d) return;
 	cudaStreamSynchronize(d->stream);
 	d->zd.lit.release();
+	d->zd.seqs.release();
+	d->zd.tabs.release();
+	d->zd.hufsave.release();
 	d->zd.queue.release();
 	zg_b3work_free(d->b3);
 	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->d_archive,

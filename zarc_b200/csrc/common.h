@@ -76,8 +76,11 @@ size_t zg_scan_run(cudaStream_t s, ZgBuf& tiles, const u64* in, u64 n, u64 base,
 
 // ---- zstd_decode.cu ----
 struct ZgZdWork {
-	ZgBuf lit;    // per-warp literal staging
-	ZgBuf queue;  // frame queue counter
+	ZgBuf seqs;     // per-warp sequence arenas
+	ZgBuf lit;      // per-warp literal buffers
+	ZgBuf tabs;     // per-lane FSE decode-table slots
+	ZgBuf hufsave;  // per-lane Huffman weights (Treeless blocks)
+	ZgBuf queue;    // frame queue counter
 };
 size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
                           const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,

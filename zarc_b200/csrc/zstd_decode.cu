@@ -1,37 +1,115 @@
 // K5 + K6: Zstandard frame decode (RFC 8878).  Replaces DCtx::decompress_stream as driven by
 // crates/zarc/src/decode/zstd_iterator.rs:88-153 (one frame per content entry, decode/frame_iterator.rs).
 //
-// One warp per frame; blocks of a frame are decoded in order by that warp, so Treeless literals,
-// Repeat_Mode tables, repeat offsets and cross-block matches (all produced by libzstd at levels
-// 1/3/9) come for free.  Within a block: Huffman tree + FSE tables are built
-// warp-cooperatively in shared memory, the 4 literal streams are decoded by 4 lanes, the sequence
-// bitstream by lane 0 in batches of 32, and each batch is executed by the whole warp (byte-parallel
-// copies straight into the frame's output in HBM).  Frames are pulled from an atomic queue.
-// HBM traffic: C read + N written (+ literals staged through an L2-resident per-warp buffer).
+// One warp owns a batch of 32 frames, ONE FRAME PER LANE.  Everything that is inherently serial
+// inside a frame -- frame/block header parsing, the FSE sequence bitstream with its three states,
+// repeat-offset resolution -- runs lane-per-frame, so 32 serial chains advance per warp instruction.
+// Everything that is parallel inside a frame is done by the whole warp for one frame at a time:
+// Huffman/FSE table construction, the 4 literal streams, and sequence execution (literal and match
+// copies straight into the frame's output in HBM).
+//
+// A batch proceeds in rounds, one block per live frame and round:
+//   A. per frame (warp-cooperative): block header (Raw/RLE blocks are copied on the spot), literals
+//      and sequences section headers, FSE decode tables into the lane's global slot, bitstream init;
+//   B. lock-step (lane-per-frame): every lane decodes ALL sequences of its block, resolves repeat
+//      offsets and appends them, packed to 8 bytes (offset:28 | litLength:18 | matchLength:18), to
+//      the frame's span of the warp's sequence arena;
+//   C. per frame (warp-cooperative): Huffman table + the literal streams into the warp's literal
+//      buffer, then the sequences are executed 32 at a time -- so while a frame is being written its
+//      literals, its sequences and its recent output (the match sources) are cache-hot.
+// Blocks of a frame stay in order, so Treeless literals, Repeat_Mode tables, repeat offsets and
+// cross-block matches (all produced by libzstd at levels 1/3/9) work.  State that
+// must outlive a round lives in global scratch: the FSE tables (fixed slot per lane) and the Huffman
+// weights (for Treeless blocks).  A block whose sequences do not fit the arena waits for the next round.
+// HBM traffic: C read + N written (+ 8 B per sequence and the literals staged through L2).
 #include "common.h"
 #include "zstd_common.cuh"
 
 #define ZD_WARPS 4
-#define ZD_LITBUF (ZS_BLOCK_MAX + 64)
+#define ZD_SEQ_ARENA (1u << 17)          // u64 entries of sequence staging per warp (1 MiB)
+#define ZD_LITBUF (ZS_BLOCK_MAX + 64)    // bytes of literal staging per warp
+#define ZD_TAB_SLOT 1280u                // u32 entries per lane: LL 512 | ML 512 | OF 256
+#define ZD_HUFSAVE 272u                  // bytes per lane: 256 weights + count
+#define ZD_OFF_MAX ((1u << 28) - 1u)
 
 struct ZdWarp {
-	u32 ll_tab[512];
-	u32 ml_tab[512];
-	u32 of_tab[256];
-	u32 wtab[64];      // FSE table of the Huffman weights
+	u32 tab[512];      // table under construction (FSE sequence table or Huffman-weight table)
 	u16 huf[2048];     // sym | nbBits << 8
-	u32 seq_ll[32], seq_ml[32], seq_of[32];
 	u8 weights[256];
 	i16 norm[256];
 	u16 next[256];
 	u32 misc[8];
 };
 
-struct ZdState {
+// flags
+#define ZD_F_ACTIVE 1u      // frame still has blocks to decode
+#define ZD_F_LAST 2u        // the block in flight is the frame's last
+#define ZD_F_CKSUM 4u       // frame has a Content_Checksum
+#define ZD_F_HUF_OK 8u      // a Huffman table has been defined (saved weights are valid)
+#define ZD_F_LL_OK 16u
+#define ZD_F_ML_OK 32u
+#define ZD_F_OF_OK 64u
+#define ZD_F_LL_DEF 256u    // table = the predefined one (not in the slot)
+#define ZD_F_ML_DEF 512u
+#define ZD_F_OF_DEF 1024u
+#define ZD_F_HAS_CK 2048u   // checksum field was read
+
+// one frame's decoding state; lives in the registers of the frame's lane
+struct ZdLane {
+	const u8* src;
+	u8* out;
+	u64 n, ip, cap, opos, fcs;
+	u32 status, flags, fcs_len, cksum;
 	u32 rep0, rep1, rep2;
-	u32 ll_log, ml_log, of_log, huf_bits;
-	bool huf_ok, ll_ok, ml_ok, of_ok;
+	u32 ll_log, ml_log, of_log;
+	// block in flight
+	const u8* blk;      // block body
+	u32 blk_n;
+	u32 nseq, nseq_left, seq_base;
+	ZsBack b;
+	u32 sl, so, sm;
 };
+
+template <typename T>
+ZG_DEV T zd_bc(T v, int f) { return __shfl_sync(ZG_FULL, v, f); }
+ZG_DEV const u8* zd_bc(const u8* v, int f) { return (const u8*)(uintptr_t)__shfl_sync(ZG_FULL, (u64)(uintptr_t)v, f); }
+ZG_DEV u8* zd_bc(u8* v, int f) { return (u8*)(uintptr_t)__shfl_sync(ZG_FULL, (u64)(uintptr_t)v, f); }
+
+// every lane gets a copy of lane f's frame state
+ZG_DEV ZdLane zd_bcast(const ZdLane& L, int f) {
+	ZdLane U;
+	U.src = zd_bc(L.src, f);
+	U.out = zd_bc(L.out, f);
+	U.n = zd_bc(L.n, f);
+	U.ip = zd_bc(L.ip, f);
+	U.cap = zd_bc(L.cap, f);
+	U.opos = zd_bc(L.opos, f);
+	U.fcs = zd_bc(L.fcs, f);
+	U.status = zd_bc(L.status, f);
+	U.flags = zd_bc(L.flags, f);
+	U.fcs_len = zd_bc(L.fcs_len, f);
+	U.cksum = zd_bc(L.cksum, f);
+	U.rep0 = zd_bc(L.rep0, f);
+	U.rep1 = zd_bc(L.rep1, f);
+	U.rep2 = zd_bc(L.rep2, f);
+	U.ll_log = zd_bc(L.ll_log, f);
+	U.ml_log = zd_bc(L.ml_log, f);
+	U.of_log = zd_bc(L.of_log, f);
+	U.blk = zd_bc(L.blk, f);
+	U.blk_n = zd_bc(L.blk_n, f);
+	U.nseq = zd_bc(L.nseq, f);
+	U.nseq_left = zd_bc(L.nseq_left, f);
+	U.seq_base = zd_bc(L.seq_base, f);
+	U.b.start = zd_bc(L.b.start, f);
+	U.b.ptr = zd_bc(L.b.ptr, f);
+	U.b.lo = zd_bc(L.b.lo, f);
+	U.b.hi = zd_bc(L.b.hi, f);
+	U.b.consumed = zd_bc(L.b.consumed, f);
+	U.sl = zd_bc(L.sl, f);
+	U.so = zd_bc(L.so, f);
+	U.sm = zd_bc(L.sm, f);
+	return U;
+}
 
 // ---------------------------------------------------------------------------------------------
 // warp-cooperative copies
@@ -85,8 +163,9 @@ ZG_DEV void zd_warp_match(u8* d, u32 off, u32 ml) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Huffman tree description -> W->huf.  Returns bytes consumed (0 on error).  All lanes call.
-ZG_DEV u32 zd_read_huf_tree(ZdWarp* W, ZdState& st, const u8* src, u32 n) {
+// Huffman tree description -> W->weights[0..nw) (the last weight is implied).  Returns bytes
+// consumed (0 on error).  All lanes call.
+ZG_DEV u32 zd_read_huf_weights(ZdWarp* W, const u8* src, u32 n, u32* nw_out) {
 	u32 lane = zg_lane();
 	if (n < 1) return 0;
 	u32 h = src[0];
@@ -115,7 +194,7 @@ ZG_DEV u32 zd_read_huf_tree(ZdWarp* W, ZdState& st, const u8* src, u32 n) {
 		u32 nc = W->misc[0], nsym = W->misc[1], log = W->misc[2];
 		__syncwarp();
 		if (nc == 0 || nc >= csz) return 0;
-		zs_fse_build_dtable(W->wtab, W->norm, nsym, log, W->next);
+		zs_fse_build_dtable(W->tab, W->norm, nsym, log, W->next);
 		if (lane == 0) {
 			ZsBack b;
 			u32 cnt = 0;
@@ -130,19 +209,19 @@ ZG_DEV u32 zd_read_huf_tree(ZdWarp* W, ZdState& st, const u8* src, u32 n) {
 						ok = false;
 						break;
 					}
-					u32 e1 = W->wtab[s1];
+					u32 e1 = W->tab[s1];
 					W->weights[cnt++] = (u8)e1;
 					zs_back_reload(b);
 					s1 = (e1 >> 16) + zs_back_read(b, (e1 >> 8) & 0xff);
 					if (zs_back_overflow(b)) {
-						W->weights[cnt++] = (u8)W->wtab[s2];
+						W->weights[cnt++] = (u8)W->tab[s2];
 						break;
 					}
-					u32 e2 = W->wtab[s2];
+					u32 e2 = W->tab[s2];
 					W->weights[cnt++] = (u8)e2;
 					s2 = (e2 >> 16) + zs_back_read(b, (e2 >> 8) & 0xff);
 					if (zs_back_overflow(b)) {
-						W->weights[cnt++] = (u8)W->wtab[s1];
+						W->weights[cnt++] = (u8)W->tab[s1];
 						break;
 					}
 				}
@@ -154,6 +233,13 @@ ZG_DEV u32 zd_read_huf_tree(ZdWarp* W, ZdState& st, const u8* src, u32 n) {
 		__syncwarp();
 		if (nw == 0) return 0;
 	}
+	*nw_out = nw;
+	return used;
+}
+
+// W->weights[0..nw) -> W->huf.  Returns maxbits (0 on error).  All lanes call.
+ZG_DEV u32 zd_build_huf(ZdWarp* W, u32 nw) {
+	u32 lane = zg_lane();
 	// weights -> last weight, ranks, per-symbol start index (serial, <= 256 symbols)
 	if (lane == 0) {
 		u32 sum = 0;
@@ -222,9 +308,7 @@ ZG_DEV u32 zd_read_huf_tree(ZdWarp* W, ZdState& st, const u8* src, u32 n) {
 		}
 	}
 	__syncwarp();
-	st.huf_bits = maxbits;
-	st.huf_ok = true;
-	return used;
+	return maxbits;
 }
 
 // one Huffman stream, single thread
@@ -246,25 +330,23 @@ ZG_DEV bool zd_huf_stream(const u16* huf, u32 maxbits, const u8* src, u32 n, u8*
 	return zs_back_finished(b);
 }
 
-// sequence table for one of LL/OF/ML.  All lanes call.  Returns false on error; advances *pp.
-ZG_DEV bool zd_seq_table(ZdWarp* W, u32* tab, u32& log, bool& have, u32 mode, const u8*& p, const u8* end, u32 maxlog,
-                         u32 maxsym, const u32* def_tab, u32 def_log) {
+// sequence table for one of LL/OF/ML into the lane's global slot `slot`.  All lanes call (uniform).
+// Returns false on error; advances p.  `flags`: def_flag is set when the predefined table is in use.
+ZG_DEV bool zd_seq_table(ZdWarp* W, u32* slot, u32& log, u32& flags, u32 ok_flag, u32 def_flag, u32 mode, const u8*& p, const u8* end,
+                         u32 maxlog, u32 maxsym, u32 def_log) {
 	u32 lane = zg_lane();
 	if (mode == 0) {
-		for (u32 i = lane; i < (1u << def_log); i += 32) tab[i] = def_tab[i];
-		__syncwarp();
 		log = def_log;
-		have = true;
+		flags |= ok_flag | def_flag;
 		return true;
 	}
 	if (mode == 1) {
 		if (p >= end) return false;
 		u32 sym = *p++;
 		if (sym > maxsym) return false;
-		if (lane == 0) tab[0] = sym;
-		__syncwarp();
+		if (lane == 0) slot[0] = sym;
 		log = 0;
-		have = true;
+		flags = (flags | ok_flag) & ~def_flag;
 		return true;
 	}
 	if (mode == 2) {
@@ -279,107 +361,213 @@ ZG_DEV bool zd_seq_table(ZdWarp* W, u32* tab, u32& log, bool& have, u32 mode, co
 		u32 nc = W->misc[0], nsym = W->misc[1], lg = W->misc[2];
 		__syncwarp();
 		if (nc == 0) return false;
-		zs_fse_build_dtable(tab, W->norm, nsym, lg, W->next);
+		zs_fse_build_dtable(W->tab, W->norm, nsym, lg, W->next);
+		for (u32 i = lane; i < (1u << lg); i += 32) slot[i] = W->tab[i];
+		__syncwarp();
 		p += nc;
 		log = lg;
-		have = true;
+		flags = (flags | ok_flag) & ~def_flag;
 		return true;
 	}
-	return have;  // Repeat_Mode
+	return (flags & ok_flag) != 0;  // Repeat_Mode: the slot (or the predefined flag) still holds the table
 }
 
 // ---------------------------------------------------------------------------------------------
-// one Compressed block.  `out` = start of the frame's output, opos = bytes produced so far.
-ZG_DEV u32 zd_compressed_block(ZdWarp* W, ZdState& st, const u8* src, u32 n, u8* out, u64& opos, u64 cap, u8* litbuf) {
-	u32 lane = zg_lane();
-	if (n < 2) return ZS_E_CORRUPT;
-	const u8* end = src + n;
+ZG_DEV void zd_fail(ZdLane& U, u32 code) {
+	U.status = code;
+	U.flags &= ~ZD_F_ACTIVE;
+	U.nseq = U.nseq_left = 0;
+}
+// end of frame: optional checksum field, content-size check
+ZG_DEV void zd_frame_finish(ZdLane& U) {
+	U.flags &= ~ZD_F_ACTIVE;
+	U.nseq = U.nseq_left = 0;
+	if (U.flags & ZD_F_CKSUM) {
+		if (U.ip + 4 > U.n) {
+			U.status = ZS_E_SRC_SIZE;
+			return;
+		}
+		U.cksum = zg_ld32(U.src + U.ip);
+		U.flags |= ZD_F_HAS_CK;
+		U.ip += 4;
+	}
+	if (U.fcs_len && U.fcs != U.opos) U.status = ZS_E_CORRUPT;
+}
+
+// frame header (lane-private)
+ZG_DEV void zd_frame_header(ZdLane& L) {
+	const u8* src = L.src;
+	u64 n = L.n;
+	if (n < 6) return zd_fail(L, ZS_E_SRC_SIZE);
+	if (zg_ld32(src) != ZS_MAGIC) return zd_fail(L, ZS_E_PREFIX);
+	u32 desc = src[4];
+	u32 fcs_flag = desc >> 6, single = (desc >> 5) & 1, checksum = (desc >> 2) & 1, did_flag = desc & 3;
+	if (desc & 8) return zd_fail(L, ZS_E_UNSUPPORTED);
+	u64 ip = 5;
+	u64 window = 0;
+	if (!single) {
+		u32 wd = src[ip++];
+		u32 wl = 10 + (wd >> 3);
+		if (wl > 31) return zd_fail(L, ZS_E_WINDOW);
+		window = ((u64)1 << wl) + ((((u64)1 << wl) >> 3) * (wd & 7));
+	}
+	if (did_flag) {
+		u32 dl = did_flag == 3 ? 4 : did_flag;
+		if (ip + dl > n) return zd_fail(L, ZS_E_SRC_SIZE);
+		u32 did = 0;
+		for (u32 i = 0; i < dl; i++) did |= (u32)src[ip + i] << (8 * i);
+		ip += dl;
+		if (did) return zd_fail(L, ZS_E_DICT);
+	}
+	u32 fcs_len = fcs_flag == 0 ? single : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+	if (ip + fcs_len > n) return zd_fail(L, ZS_E_SRC_SIZE);
+	u64 fcs = 0;
+	for (u32 i = 0; i < fcs_len; i++) fcs |= (u64)src[ip + i] << (8 * i);
+	if (fcs_len == 2) fcs += 256;
+	ip += fcs_len;
+	// libzstd's streaming decoder (what zstd_iterator.rs:29 creates) refuses windows > 2^27
+	// ("Frame requires too much memory for decoding", SURVEY.md App. C)
+	if ((single ? fcs : window) > ((u64)1 << 27)) return zd_fail(L, ZS_E_WINDOW);
+	L.ip = ip;
+	L.fcs = fcs;
+	L.fcs_len = fcs_len;
+	if (checksum) L.flags |= ZD_F_CKSUM;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Literals_Section_Header (RFC 8878 §3.1.1.3.1.1).  Returns false on a malformed header.
+struct ZdLitHdr {
+	u32 ltype, regen, comp, hdr, streams;
+};
+ZG_DEV bool zd_lit_header(const u8* src, u32 n, ZdLitHdr& h) {
+	if (n < 2) return false;
 	u32 b0 = src[0];
-	u32 ltype = b0 & 3, sf = (b0 >> 2) & 3;
-	u32 regen = 0, comp = 0, hdr = 0, streams = 1;
-	const u8* lit = litbuf;
-	bool lit_rle = false;
-	u32 rle_byte = 0;
-	const u8* p;
-	if (ltype < 2) {
+	u32 sf = (b0 >> 2) & 3;
+	h.ltype = b0 & 3;
+	h.comp = 0;
+	h.streams = 1;
+	if (h.ltype < 2) {
 		if (sf == 0 || sf == 2) {
-			regen = b0 >> 3;
-			hdr = 1;
+			h.regen = b0 >> 3;
+			h.hdr = 1;
 		} else if (sf == 1) {
-			regen = (b0 >> 4) | ((u32)src[1] << 4);
-			hdr = 2;
+			h.regen = (b0 >> 4) | ((u32)src[1] << 4);
+			h.hdr = 2;
 		} else {
-			if (n < 3) return ZS_E_CORRUPT;
-			regen = (b0 >> 4) | ((u32)src[1] << 4) | ((u32)src[2] << 12);
-			hdr = 3;
+			if (n < 3) return false;
+			h.regen = (b0 >> 4) | ((u32)src[1] << 4) | ((u32)src[2] << 12);
+			h.hdr = 3;
 		}
-		if (regen > ZS_BLOCK_MAX) return ZS_E_CORRUPT;
-		p = src + hdr;
-		if (ltype == 0) {
-			if (hdr + regen > n) return ZS_E_CORRUPT;
-			lit = p;
-			p += regen;
-		} else {
-			if (hdr + 1 > n) return ZS_E_CORRUPT;
-			lit_rle = true;
-			rle_byte = *p++;
-		}
+		if (h.regen > ZS_BLOCK_MAX) return false;
+		h.comp = h.ltype == 0 ? h.regen : 1;
+		return h.hdr + h.comp <= n;
+	}
+	if (n < 3) return false;
+	u64 v = (u64)b0 | ((u64)src[1] << 8) | ((u64)src[2] << 16);
+	if (sf == 0 || sf == 1) {
+		h.regen = (u32)(v >> 4) & 1023;
+		h.comp = (u32)(v >> 14) & 1023;
+		h.hdr = 3;
+		h.streams = sf == 0 ? 1 : 4;
+	} else if (sf == 2) {
+		if (n < 4) return false;
+		v |= (u64)src[3] << 24;
+		h.regen = (u32)(v >> 4) & 16383;
+		h.comp = (u32)(v >> 18) & 16383;
+		h.hdr = 4;
+		h.streams = 4;
 	} else {
-		if (n < 3) return ZS_E_CORRUPT;
-		u64 v = (u64)b0 | ((u64)src[1] << 8) | ((u64)src[2] << 16);
-		if (sf == 0 || sf == 1) {
-			regen = (u32)(v >> 4) & 1023;
-			comp = (u32)(v >> 14) & 1023;
-			hdr = 3;
-			streams = sf == 0 ? 1 : 4;
-		} else if (sf == 2) {
-			if (n < 4) return ZS_E_CORRUPT;
-			v |= (u64)src[3] << 24;
-			regen = (u32)(v >> 4) & 16383;
-			comp = (u32)(v >> 18) & 16383;
-			hdr = 4;
-			streams = 4;
-		} else {
-			if (n < 5) return ZS_E_CORRUPT;
-			v |= ((u64)src[3] << 24) | ((u64)src[4] << 32);
-			regen = (u32)(v >> 4) & 262143;
-			comp = (u32)(v >> 22) & 262143;
-			hdr = 5;
-			streams = 4;
-		}
-		if (regen > ZS_BLOCK_MAX || hdr + comp > n || regen == 0) return ZS_E_CORRUPT;
-		const u8* lp = src + hdr;
-		const u8* lend = lp + comp;
-		if (ltype == 2) {
-			u32 used = zd_read_huf_tree(W, st, lp, comp);
-			if (used == 0) return ZS_E_CORRUPT;
-			lp += used;
-		} else if (!st.huf_ok) {
-			return ZS_E_CORRUPT;
-		}
-		bool ok = true;
-		if (streams == 1) {
-			if (lane == 0) ok = zd_huf_stream(W->huf, st.huf_bits, lp, (u32)(lend - lp), litbuf, regen);
-		} else {
-			if (lend - lp < 10) return ZS_E_CORRUPT;
-			u32 s1 = zg_ld16(lp), s2 = zg_ld16(lp + 2), s3 = zg_ld16(lp + 4);
-			lp += 6;
-			u32 avail = (u32)(lend - lp);
-			u32 seg = (regen + 3) >> 2;
-			if (s1 + s2 + s3 >= avail || seg * 3 > regen) return ZS_E_CORRUPT;
-			if (lane < 4) {
-				u32 so = lane == 0 ? 0 : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
-				u32 sn = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : avail - s1 - s2 - s3;
-				u32 cnt = lane < 3 ? seg : regen - 3 * seg;
-				ok = zd_huf_stream(W->huf, st.huf_bits, lp + so, sn, litbuf + lane * seg, cnt);
+		if (n < 5) return false;
+		v |= ((u64)src[3] << 24) | ((u64)src[4] << 32);
+		h.regen = (u32)(v >> 4) & 262143;
+		h.comp = (u32)(v >> 22) & 262143;
+		h.hdr = 5;
+		h.streams = 4;
+	}
+	return h.regen <= ZS_BLOCK_MAX && h.hdr + h.comp <= n && h.regen != 0;
+}
+
+// The block's literals (uniform in the warp): Raw -> pointer into the block, RLE -> the byte,
+// Huffman -> decoded into litbuf.  Returns a ZS_E_* code.
+ZG_DEV u32 zd_literals(ZdWarp* W, u32& flags, const u8* src, const ZdLitHdr& h, bool last, u8* litbuf, u8* hufsave, const u8*& lit,
+                       bool& lit_rle, u32& rle_byte) {
+	u32 lane = zg_lane();
+	lit_rle = false;
+	rle_byte = 0;
+	if (h.ltype == 0) {
+		lit = src + h.hdr;
+		return ZS_OK;
+	}
+	if (h.ltype == 1) {
+		lit_rle = true;
+		rle_byte = src[h.hdr];
+		lit = src;
+		return ZS_OK;
+	}
+	const u8* lp = src + h.hdr;
+	const u8* lend = lp + h.comp;
+	u32 regen = h.regen;
+	u32 huf_bits;
+	if (h.ltype == 2) {
+		u32 nw = 0;
+		u32 used = zd_read_huf_weights(W, lp, h.comp, &nw);
+		if (used == 0) return ZS_E_CORRUPT;
+		if (!last) {  // a later Treeless block may need this tree again
+			for (u32 i = lane; i < nw; i += 32) hufsave[i] = W->weights[i];
+			if (lane == 0) {
+				hufsave[256] = (u8)nw;
+				hufsave[257] = (u8)(nw >> 8);
 			}
 		}
-		if (!__all_sync(ZG_FULL, ok)) return ZS_E_CORRUPT;
-		p = lend;
+		huf_bits = zd_build_huf(W, nw);
+		if (huf_bits == 0) return ZS_E_CORRUPT;
+		flags |= ZD_F_HUF_OK;
+		lp += used;
+	} else {
+		if (!(flags & ZD_F_HUF_OK)) return ZS_E_CORRUPT;
+		u32 nw = (u32)hufsave[256] | ((u32)hufsave[257] << 8);
+		__syncwarp();
+		for (u32 i = lane; i < nw; i += 32) W->weights[i] = hufsave[i];
+		__syncwarp();
+		huf_bits = zd_build_huf(W, nw);
+		if (huf_bits == 0) return ZS_E_CORRUPT;
 	}
+	bool ok = true;
+	if (h.streams == 1) {
+		if (lane == 0) ok = zd_huf_stream(W->huf, huf_bits, lp, (u32)(lend - lp), litbuf, regen);
+	} else {
+		if (lend - lp < 10) return ZS_E_CORRUPT;
+		u32 s1 = zg_ld16(lp), s2 = zg_ld16(lp + 2), s3 = zg_ld16(lp + 4);
+		lp += 6;
+		u32 avail = (u32)(lend - lp);
+		u32 seg = (regen + 3) >> 2;
+		if (s1 + s2 + s3 >= avail || seg * 3 > regen) return ZS_E_CORRUPT;
+		if (lane < 4) {
+			u32 so = lane == 0 ? 0 : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
+			u32 sn = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : avail - s1 - s2 - s3;
+			u32 cnt = lane < 3 ? seg : regen - 3 * seg;
+			ok = zd_huf_stream(W->huf, huf_bits, lp + so, sn, litbuf + lane * seg, cnt);
+		}
+	}
+	if (!__all_sync(ZG_FULL, ok)) return ZS_E_CORRUPT;
 	__syncwarp();
-	// ---- sequences section ----
-	if (p >= end) return ZS_E_CORRUPT;
+	lit = litbuf;
+	return ZS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A for one Compressed block of the frame viewed by U (uniform in the warp).  Returns 0 = ok
+// (U.nseq sequences wait for phase B; 0 means the block was literals only and is complete),
+// ZD_DEFER = the sequence arena is full (nothing consumed), else a ZS_E_* code + 1.
+#define ZD_DEFER 1u
+#define ZD_ERR(c) ((c) + 1u)
+ZG_DEV u32 zd_block_setup(ZdWarp* W, ZdLane& U, const u8* src, u32 n, bool last, u32* slot, u32& arena_used, u8* litbuf, u8* hufsave) {
+	ZdLitHdr h;
+	if (!zd_lit_header(src, n, h)) return ZD_ERR(ZS_E_CORRUPT);
+	const u8* end = src + n;
+	const u8* p = src + h.hdr + h.comp;
+	// ---- sequences section header ----
+	if (p >= end) return ZD_ERR(ZS_E_CORRUPT);
 	u32 nseq;
 	{
 		u32 c0 = p[0];
@@ -387,293 +575,357 @@ ZG_DEV u32 zd_compressed_block(ZdWarp* W, ZdState& st, const u8* src, u32 n, u8*
 			nseq = c0;
 			p += 1;
 		} else if (c0 < 255) {
-			if (end - p < 2) return ZS_E_CORRUPT;
+			if (end - p < 2) return ZD_ERR(ZS_E_CORRUPT);
 			nseq = ((c0 - 128) << 8) + p[1];
 			p += 2;
 		} else {
-			if (end - p < 3) return ZS_E_CORRUPT;
+			if (end - p < 3) return ZD_ERR(ZS_E_CORRUPT);
 			nseq = (u32)p[1] + ((u32)p[2] << 8) + 0x7F00;
 			p += 3;
 		}
 	}
-	u32 lpos = 0;
-	u64 o = opos;
-	if (nseq) {
-		if (p >= end) return ZS_E_CORRUPT;
-		u32 modes = *p++;
-		if (modes & 3) return ZS_E_CORRUPT;
-		if (!zd_seq_table(W, W->ll_tab, st.ll_log, st.ll_ok, (modes >> 6) & 3, p, end, ZS_LL_MAXLOG, 35, ZS_LL_DEFAULT_DTABLE, 6)) return ZS_E_CORRUPT;
-		if (!zd_seq_table(W, W->of_tab, st.of_log, st.of_ok, (modes >> 4) & 3, p, end, ZS_OF_MAXLOG, 31, ZS_OF_DEFAULT_DTABLE, 5)) return ZS_E_CORRUPT;
-		if (!zd_seq_table(W, W->ml_tab, st.ml_log, st.ml_ok, (modes >> 2) & 3, p, end, ZS_ML_MAXLOG, 52, ZS_ML_DEFAULT_DTABLE, 6)) return ZS_E_CORRUPT;
-		// lane 0 owns the bitstream, the three states and the repeat offsets
-		ZsBack b;
-		u32 sl = 0, so = 0, sm = 0;
-		u32 rep0 = st.rep0, rep1 = st.rep1, rep2 = st.rep2;
-		bool ok = true;
-		if (lane == 0) {
-			ok = zs_back_init(b, p, (u32)(end - p));
-			if (ok) {
-				zs_back_reload(b);
-				sl = zs_back_read(b, st.ll_log);
-				so = zs_back_read(b, st.of_log);
-				sm = zs_back_read(b, st.ml_log);
-				ok = !zs_back_overflow(b);
-			}
+	if (nseq == 0) {
+		if (p != end) return ZD_ERR(ZS_E_CORRUPT);
+		const u8* lit;
+		bool lit_rle;
+		u32 rle_byte;
+		u32 r = zd_literals(W, U.flags, src, h, last, litbuf, hufsave, lit, lit_rle, rle_byte);
+		if (r) return ZD_ERR(r);
+		if (U.opos + h.regen > U.cap) return ZD_ERR(ZS_E_DST_SMALL);
+		if (h.regen) {
+			if (lit_rle) zg_warp_fill(U.out + U.opos, rle_byte, h.regen);
+			else zg_warp_copy(U.out + U.opos, lit, h.regen);
 		}
-		if (!__all_sync(ZG_FULL, ok)) return ZS_E_CORRUPT;
-		for (u32 s0 = 0; s0 < nseq; s0 += 32) {
-			u32 cnt = zg_min<u32>(32u, nseq - s0);
-			if (lane == 0) {
-				for (u32 k = 0; k < cnt; k++) {
-					u32 oe = W->of_tab[so], me = W->ml_tab[sm], le = W->ll_tab[sl];
-					u32 oc = oe & 0xff, mc = me & 0xff, lc = le & 0xff;
-					if (oc > 31 || mc > 52 || lc > 35) {
-						ok = false;
-						break;
-					}
-					zs_back_reload(b);  // >= 57 bits available from here
-					u32 ofv = (1u << oc) + zs_back_read(b, oc);
-					u32 used = oc;
-					if (oc > 24) {
-						zs_back_reload(b);
-						used = 0;
-					}
-					u32 mb = ZS_ML_BITS[mc], lb = ZS_LL_BITS[lc];
-					u32 ml = ZS_ML_BASE[mc] + zs_back_read(b, mb);
-					u32 ll = ZS_LL_BASE[lc] + zs_back_read(b, lb);
-					used += mb + lb;
-					if (s0 + k + 1 < nseq) {
-						if (used > 30) zs_back_reload(b);  // the three state updates need <= 26 bits
-						sl = (le >> 16) + zs_back_read(b, (le >> 8) & 0xff);
-						sm = (me >> 16) + zs_back_read(b, (me >> 8) & 0xff);
-						so = (oe >> 16) + zs_back_read(b, (oe >> 8) & 0xff);
-					}
-					if (zs_back_overflow(b)) {
-						ok = false;
-						break;
-					}
-					// repeat-offset resolution (RFC 8878 §3.1.1.5)
-					u32 off;
-					if (ofv > 3) {
-						off = ofv - 3;
-						rep2 = rep1;
-						rep1 = rep0;
-						rep0 = off;
-					} else {
-						u32 idx = ofv - 1 + (ll == 0 ? 1 : 0);
-						if (idx == 0) {
-							off = rep0;
-						} else {
-							off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-							if (off == 0) {
-								ok = false;
-								break;
-							}
-							if (idx > 1) rep2 = rep1;
-							rep1 = rep0;
-							rep0 = off;
-						}
-					}
-					W->seq_ll[k] = ll;
-					W->seq_ml[k] = ml;
-					W->seq_of[k] = off;
-				}
-				if (ok && s0 + cnt == nseq) {
-					zs_back_reload(b);
-					ok = zs_back_finished(b);
-				}
-			}
-			if (!__all_sync(ZG_FULL, ok)) return ZS_E_CORRUPT;
-			__syncwarp();  // lane 0's batch in shared memory is visible to the warp
-			// execute the batch: one sequence per lane.  Output and literal positions come from warp
-			// scans; (a) all literal runs and (b) all matches whose source lies wholly before this
-			// batch's output are independent and copied lane-parallel; (c) the remaining matches
-			// (sources inside the batch, incl. overlapping ones) go in order, warp-cooperatively.
-			{
-				bool act = lane < cnt;
-				u32 ll = act ? W->seq_ll[lane] : 0, ml = act ? W->seq_ml[lane] : 0, of = act ? W->seq_of[lane] : 0;
-				u32 incl = zg_warp_incl_scan(ll + ml), lincl = zg_warp_incl_scan(ll);
-				u32 btot = __shfl_sync(ZG_FULL, incl, 31), ltot = __shfl_sync(ZG_FULL, lincl, 31);
-				if (lpos + ltot > regen) return ZS_E_CORRUPT;
-				if (o + btot > cap) return ZS_E_DST_SMALL;
-				u64 mstart = o + (incl - ll - ml) + ll;  // where my match begins in the frame output
-				if (__any_sync(ZG_FULL, act && (u64)of > mstart)) return ZS_E_CORRUPT;
-				u8* d = out + mstart - ll;
-				u32 lsrc = lpos + (lincl - ll);
-				// (a) literals
-				u32 longl = __ballot_sync(ZG_FULL, ll >= 48);
-				if (ll < 48) {
-					if (lit_rle) for (u32 k = 0; k < ll; k++) d[k] = (u8)rle_byte;
-					else for (u32 k = 0; k < ll; k++) d[k] = lit[lsrc + k];
-				}
-				while (longl) {
-					int l = __ffs((int)longl) - 1;
-					longl &= longl - 1;
-					u32 n2 = __shfl_sync(ZG_FULL, ll, l), s2 = __shfl_sync(ZG_FULL, lsrc, l);
-					u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)d, l);
-					if (lit_rle) zg_warp_fill((u8*)(uintptr_t)d2, rle_byte, n2);
-					else zg_warp_copy((u8*)(uintptr_t)d2, lit + s2, n2);
-				}
-				// (b) independent matches
-				u8* md = out + mstart;
-				bool indep = act && ml > 0 && mstart - of + ml <= o;
-				u32 longm = __ballot_sync(ZG_FULL, indep && ml >= 48);
-				if (indep && ml < 48) {
-					const u8* ms = md - of;
-					for (u32 k = 0; k < ml; k++) md[k] = ms[k];
-				}
-				while (longm) {
-					int l = __ffs((int)longm) - 1;
-					longm &= longm - 1;
-					u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
-					u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
-					zg_warp_copy((u8*)(uintptr_t)d2, (const u8*)(uintptr_t)d2 - o2, n2);
-				}
-				__syncwarp();
-				// (c) dependent matches, in sequence order
-				u32 dep = __ballot_sync(ZG_FULL, act && ml > 0 && !indep);
-				while (dep) {
-					int l = __ffs((int)dep) - 1;
-					dep &= dep - 1;
-					u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
-					u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
-					zd_warp_match((u8*)(uintptr_t)d2, o2, n2);
-					__syncwarp();
-				}
-				o += btot;
-				lpos += ltot;
-			}
-			__syncwarp();
-		}
-		st.rep0 = __shfl_sync(ZG_FULL, rep0, 0);
-		st.rep1 = __shfl_sync(ZG_FULL, rep1, 0);
-		st.rep2 = __shfl_sync(ZG_FULL, rep2, 0);
-	} else if (p != end) {
-		return ZS_E_CORRUPT;
+		U.opos += h.regen;
+		U.nseq = U.nseq_left = 0;
+		__syncwarp();
+		return 0;
 	}
-	u32 rest = regen - lpos;
-	if (o + rest > cap) return ZS_E_DST_SMALL;
-	if (rest) {
-		if (lit_rle) zg_warp_fill(out + o, rle_byte, rest);
-		else zg_warp_copy(out + o, lit + lpos, rest);
-		o += rest;
-	}
-	if (o - opos > ZS_BLOCK_MAX) return ZS_E_CORRUPT;
+	if (nseq > ZD_SEQ_ARENA) return ZD_ERR(ZS_E_CORRUPT);  // > 131072 sequences cannot come from a 128 KiB block
+	if (arena_used + nseq > ZD_SEQ_ARENA) return ZD_DEFER;    // (an empty arena always fits a block)
+	if (p >= end) return ZD_ERR(ZS_E_CORRUPT);
+	u32 modes = *p++;
+	if (modes & 3) return ZD_ERR(ZS_E_CORRUPT);
+	if (!zd_seq_table(W, slot, U.ll_log, U.flags, ZD_F_LL_OK, ZD_F_LL_DEF, (modes >> 6) & 3, p, end, ZS_LL_MAXLOG, 35, 6)) return ZD_ERR(ZS_E_CORRUPT);
+	if (!zd_seq_table(W, slot + 1024, U.of_log, U.flags, ZD_F_OF_OK, ZD_F_OF_DEF, (modes >> 4) & 3, p, end, ZS_OF_MAXLOG, 31, 5)) return ZD_ERR(ZS_E_CORRUPT);
+	if (!zd_seq_table(W, slot + 512, U.ml_log, U.flags, ZD_F_ML_OK, ZD_F_ML_DEF, (modes >> 2) & 3, p, end, ZS_ML_MAXLOG, 52, 6)) return ZD_ERR(ZS_E_CORRUPT);
+	// bitstream + the three initial states (uniform here; the frame's lane keeps them)
+	if (!zs_back_init(U.b, p, (u32)(end - p))) return ZD_ERR(ZS_E_CORRUPT);
+	zs_back_reload(U.b);
+	U.sl = zs_back_read(U.b, U.ll_log);
+	U.so = zs_back_read(U.b, U.of_log);
+	U.sm = zs_back_read(U.b, U.ml_log);
+	if (zs_back_overflow(U.b)) return ZD_ERR(ZS_E_CORRUPT);
+	U.nseq = U.nseq_left = nseq;
+	U.seq_base = arena_used;
+	U.blk = src;
+	U.blk_n = n;
+	arena_used += nseq;
 	__syncwarp();
-	opos = o;
-	return ZS_OK;
+	return 0;
 }
 
-// one frame.  Returns status; *produced = bytes written; *cksum = stored checksum (valid if *has_ck).
-ZG_DEV u32 zd_frame(ZdWarp* W, const u8* src, u64 n, u8* out, u64 cap, u8* litbuf, u64* produced, u32* cksum, bool* has_ck) {
-	*produced = 0;
-	*has_ck = false;
-	if (n < 6) return ZS_E_SRC_SIZE;
-	if (zg_ld32(src) != ZS_MAGIC) return ZS_E_PREFIX;
-	u32 desc = src[4];
-	u32 fcs_flag = desc >> 6, single = (desc >> 5) & 1, checksum = (desc >> 2) & 1, did_flag = desc & 3;
-	if (desc & 8) return ZS_E_UNSUPPORTED;
-	u64 ip = 5;
-	u64 window = 0;
-	if (!single) {
-		u32 wd = src[ip++];
-		u32 wl = 10 + (wd >> 3);
-		if (wl > 31) return ZS_E_WINDOW;
-		window = ((u64)1 << wl) + ((((u64)1 << wl) >> 3) * (wd & 7));
-	}
-	if (did_flag) {
-		u32 dl = did_flag == 3 ? 4 : did_flag;
-		if (ip + dl > n) return ZS_E_SRC_SIZE;
-		u32 did = 0;
-		for (u32 i = 0; i < dl; i++) did |= (u32)src[ip + i] << (8 * i);
-		ip += dl;
-		if (did) return ZS_E_DICT;
-	}
-	u32 fcs_len = fcs_flag == 0 ? single : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
-	if (ip + fcs_len > n) return ZS_E_SRC_SIZE;
-	u64 fcs = 0;
-	for (u32 i = 0; i < fcs_len; i++) fcs |= (u64)src[ip + i] << (8 * i);
-	if (fcs_len == 2) fcs += 256;
-	ip += fcs_len;
-	// libzstd's streaming decoder (what zstd_iterator.rs:29 creates) refuses windows > 2^27
-	// ("Frame requires too much memory for decoding", SURVEY.md App. C)
-	if ((single ? fcs : window) > ((u64)1 << 27)) return ZS_E_WINDOW;
-	ZdState st;
-	st.rep0 = 1;
-	st.rep1 = 4;
-	st.rep2 = 8;
-	st.huf_ok = st.ll_ok = st.ml_ok = st.of_ok = false;
-	st.ll_log = st.ml_log = st.of_log = st.huf_bits = 0;
-	u64 opos = 0;
+// Advance the frame viewed by U (uniform) through its blocks until one with sequences is ready for
+// phase B, the frame ends, fails, or has to wait for arena space.
+ZG_DEV void zd_setup_frame(ZdWarp* W, ZdLane& U, u32* slot, u32& arena_used, u8* litbuf, u8* hufsave) {
 	for (;;) {
-		if (ip + 3 > n) return ZS_E_SRC_SIZE;
-		u32 bh = zg_ld24(src + ip);
-		ip += 3;
+		if (U.ip + 3 > U.n) return zd_fail(U, ZS_E_SRC_SIZE);
+		u32 bh = zg_ld24(U.src + U.ip);
 		u32 last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
-		if (type == 3) return ZS_E_CORRUPT;
+		if (type == 3) return zd_fail(U, ZS_E_CORRUPT);
+		u64 body = U.ip + 3;
 		if (type == 0) {
-			if (ip + bsize > n) return ZS_E_SRC_SIZE;
-			if (bsize > ZS_BLOCK_MAX) return ZS_E_CORRUPT;
-			if (opos + bsize > cap) return ZS_E_DST_SMALL;
-			zg_warp_copy(out + opos, src + ip, bsize);
-			opos += bsize;
-			ip += bsize;
+			if (body + bsize > U.n) return zd_fail(U, ZS_E_SRC_SIZE);
+			if (bsize > ZS_BLOCK_MAX) return zd_fail(U, ZS_E_CORRUPT);
+			if (U.opos + bsize > U.cap) return zd_fail(U, ZS_E_DST_SMALL);
+			zg_warp_copy(U.out + U.opos, U.src + body, bsize);
+			U.opos += bsize;
+			U.ip = body + bsize;
 		} else if (type == 1) {
-			if (ip + 1 > n) return ZS_E_SRC_SIZE;
-			if (bsize > ZS_BLOCK_MAX) return ZS_E_CORRUPT;
-			if (opos + bsize > cap) return ZS_E_DST_SMALL;
-			zg_warp_fill(out + opos, src[ip], bsize);
-			opos += bsize;
-			ip += 1;
+			if (body + 1 > U.n) return zd_fail(U, ZS_E_SRC_SIZE);
+			if (bsize > ZS_BLOCK_MAX) return zd_fail(U, ZS_E_CORRUPT);
+			if (U.opos + bsize > U.cap) return zd_fail(U, ZS_E_DST_SMALL);
+			zg_warp_fill(U.out + U.opos, U.src[body], bsize);
+			U.opos += bsize;
+			U.ip = body + 1;
 		} else {
-			if (bsize > ZS_BLOCK_MAX) return ZS_E_CORRUPT;
-			if (ip + bsize > n) return ZS_E_SRC_SIZE;
-			u32 r = zd_compressed_block(W, st, src + ip, bsize, out, opos, cap, litbuf);
-			if (r) return r;
-			ip += bsize;
+			if (bsize > ZS_BLOCK_MAX) return zd_fail(U, ZS_E_CORRUPT);
+			if (body + bsize > U.n) return zd_fail(U, ZS_E_SRC_SIZE);
+			u32 r = zd_block_setup(W, U, U.src + body, bsize, last != 0, slot, arena_used, litbuf, hufsave);
+			if (r == ZD_DEFER) return;
+			if (r) return zd_fail(U, r - 1u);
+			U.ip = body + bsize;
+			if (U.nseq) {
+				U.flags = last ? (U.flags | ZD_F_LAST) : (U.flags & ~ZD_F_LAST);
+				return;
+			}
 		}
 		__syncwarp();
-		if (last) break;
+		if (last) return zd_frame_finish(U);
 	}
-	if (checksum) {
-		if (ip + 4 > n) return ZS_E_SRC_SIZE;
-		*cksum = zg_ld32(src + ip);
-		*has_ck = true;
-		ip += 4;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase B, lane-private: decode up to `cnt` sequences of this lane's block and append them, packed,
+// to dst.  The caller keeps all lanes in step (cnt is bounded) so that the warp stays converged.
+ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, const u32* oft, u64* dst) {
+	ZsBack b = L.b;
+	u32 sl = L.sl, so = L.so, sm = L.sm;
+	u32 rep0 = L.rep0, rep1 = L.rep1, rep2 = L.rep2;
+	u32 left = L.nseq_left;
+	for (u32 k = 0; k < cnt; k++) {
+		u32 oe = oft[so], me = mlt[sm], le = llt[sl];
+		u32 oc = oe & 0xff, mc = me & 0xff, lc = le & 0xff;
+		if (oc > 31 || mc > 52 || lc > 35) return false;
+		zs_back_reload(b);  // >= 57 bits available from here
+		u32 ofv = (1u << oc) + zs_back_read(b, oc);
+		u32 used = oc;
+		if (oc > 24) {
+			zs_back_reload(b);
+			used = 0;
+		}
+		u32 mb = ZS_ML_BITS[mc], lb = ZS_LL_BITS[lc];
+		u32 ml = ZS_ML_BASE[mc] + zs_back_read(b, mb);
+		u32 ll = ZS_LL_BASE[lc] + zs_back_read(b, lb);
+		used += mb + lb;
+		if (left - k > 1) {
+			if (used > 30) zs_back_reload(b);  // the three state updates need <= 26 bits
+			sl = (le >> 16) + zs_back_read(b, (le >> 8) & 0xff);
+			sm = (me >> 16) + zs_back_read(b, (me >> 8) & 0xff);
+			so = (oe >> 16) + zs_back_read(b, (oe >> 8) & 0xff);
+		}
+		if (zs_back_overflow(b)) return false;
+		// repeat-offset resolution (RFC 8878 §3.1.1.5)
+		u32 off;
+		if (ofv > 3) {
+			off = ofv - 3;
+			rep2 = rep1;
+			rep1 = rep0;
+			rep0 = off;
+		} else {
+			u32 idx = ofv - 1 + (ll == 0 ? 1 : 0);
+			if (idx == 0) {
+				off = rep0;
+			} else {
+				off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
+				if (off == 0) return false;
+				if (idx > 1) rep2 = rep1;
+				rep1 = rep0;
+				rep0 = off;
+			}
+		}
+		// offsets beyond 2^28 exceed every window this decoder accepts; lengths are < 2^18 by construction
+		if (off > ZD_OFF_MAX) return false;
+		dst[k] = (u64)off | ((u64)ll << 28) | ((u64)ml << 46);
 	}
-	*produced = opos;
-	if (fcs_len && fcs != opos) return ZS_E_CORRUPT;
+	left -= cnt;
+	if (left == 0) {
+		zs_back_reload(b);
+		if (!zs_back_finished(b)) return false;
+	}
+	L.b = b;
+	L.sl = sl;
+	L.so = so;
+	L.sm = sm;
+	L.rep0 = rep0;
+	L.rep1 = rep1;
+	L.rep2 = rep2;
+	L.nseq_left = left;
+	return true;
+}
+
+// Phase C: execute `cnt` (<= 32) sequences, one per lane.  Output and literal positions come from
+// warp scans; (a) all literal runs and (b) all matches whose source lies wholly before this batch's
+// output are independent and copied lane-parallel; (c) the remaining matches (sources inside the
+// batch, incl. overlapping ones) go in order, warp-cooperatively.
+ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte, u32 regen,
+                       u32& lpos_io) {
+	u32 lane = zg_lane();
+	u64 o = o_io;
+	u32 lpos = lpos_io;
+	bool act = lane < cnt;
+	u64 sq = act ? seqs[lane] : 0;
+	u32 of = (u32)sq & ZD_OFF_MAX, ll = (u32)(sq >> 28) & 0x3ffffu, ml = (u32)(sq >> 46);
+	u32 incl = zg_warp_incl_scan(ll + ml), lincl = zg_warp_incl_scan(ll);
+	u32 btot = __shfl_sync(ZG_FULL, incl, 31), ltot = __shfl_sync(ZG_FULL, lincl, 31);
+	if (lpos + ltot > regen) return ZS_E_CORRUPT;
+	if (o + btot > cap) return ZS_E_DST_SMALL;
+	u64 mstart = o + (incl - ll - ml) + ll;  // where my match begins in the frame output
+	if (__any_sync(ZG_FULL, act && (u64)of > mstart)) return ZS_E_CORRUPT;
+	u8* d = out + mstart - ll;
+	u32 lsrc = lpos + (lincl - ll);
+	// (a) literals
+	u32 longl = __ballot_sync(ZG_FULL, ll >= 48);
+	if (ll < 48) {
+		if (lit_rle) for (u32 k = 0; k < ll; k++) d[k] = (u8)rle_byte;
+		else for (u32 k = 0; k < ll; k++) d[k] = lit[lsrc + k];
+	}
+	while (longl) {
+		int l = __ffs((int)longl) - 1;
+		longl &= longl - 1;
+		u32 n2 = __shfl_sync(ZG_FULL, ll, l), s2 = __shfl_sync(ZG_FULL, lsrc, l);
+		u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)d, l);
+		if (lit_rle) zg_warp_fill((u8*)(uintptr_t)d2, rle_byte, n2);
+		else zg_warp_copy((u8*)(uintptr_t)d2, lit + s2, n2);
+	}
+	// (b) independent matches
+	u8* md = out + mstart;
+	bool indep = act && ml > 0 && mstart - of + ml <= o;
+	u32 longm = __ballot_sync(ZG_FULL, indep && ml >= 48);
+	if (indep && ml < 48) {
+		const u8* ms = md - of;
+		for (u32 k = 0; k < ml; k++) md[k] = ms[k];
+	}
+	while (longm) {
+		int l = __ffs((int)longm) - 1;
+		longm &= longm - 1;
+		u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
+		u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
+		zg_warp_copy((u8*)(uintptr_t)d2, (const u8*)(uintptr_t)d2 - o2, n2);
+	}
+	__syncwarp();
+	// (c) dependent matches, in sequence order
+	u32 dep = __ballot_sync(ZG_FULL, act && ml > 0 && !indep);
+	while (dep) {
+		int l = __ffs((int)dep) - 1;
+		dep &= dep - 1;
+		u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
+		u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
+		zd_warp_match((u8*)(uintptr_t)d2, o2, n2);
+		__syncwarp();
+	}
+	o_io = o + btot;
+	lpos_io = lpos + ltot;
 	return ZS_OK;
 }
 
+// Phase C for the block in flight of the frame viewed by U (uniform): literals, then all sequences.
+ZG_DEV void zd_exec_block(ZdWarp* W, ZdLane& U, const u64* seqs, u8* litbuf, u8* hufsave) {
+	ZdLitHdr h;
+	zd_lit_header(U.blk, U.blk_n, h);  // validated in phase A
+	const u8* lit;
+	bool lit_rle;
+	u32 rle_byte;
+	u32 r = zd_literals(W, U.flags, U.blk, h, (U.flags & ZD_F_LAST) != 0, litbuf, hufsave, lit, lit_rle, rle_byte);
+	if (r) return zd_fail(U, r);
+	u64 o = U.opos;
+	u32 lpos = 0;
+	for (u32 s0 = 0; s0 < U.nseq; s0 += 32) {
+		r = zd_exec_row(seqs + s0, zg_min<u32>(32u, U.nseq - s0), U.out, o, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
+		if (r) return zd_fail(U, r);
+	}
+	// the literals after the last sequence
+	u32 rest = h.regen - lpos;
+	if (o + rest > U.cap) return zd_fail(U, ZS_E_DST_SMALL);
+	if (rest) {
+		if (lit_rle) zg_warp_fill(U.out + o, rle_byte, rest);
+		else zg_warp_copy(U.out + o, lit + lpos, rest);
+		o += rest;
+	}
+	if (o - U.opos > ZS_BLOCK_MAX) return zd_fail(U, ZS_E_CORRUPT);
+	__syncwarp();
+	U.opos = o;
+	U.nseq = 0;
+	if (U.flags & ZD_F_LAST) zd_frame_finish(U);
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ZD_WARPS * 32)
 k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
                      const u64* __restrict__ ulen, const u64* __restrict__ out_off, u64 nframes, u8* out, u64 out_cap,
-                     u8* litbufs, u32* queue, u32* status, u64* produced, u32* cksums) {
-	__shared__ ZdWarp sm[ZD_WARPS];
+                     u64* seq_arenas, u8* litbufs, u32* tabs, u8* hufsaves, u32* queue, u32* status, u64* produced, u32* cksums) {
+	ZG_DYN_SMEM(ZdWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZdWarp* W = &sm[warp];
-	u8* litbuf = litbufs + (size_t)(blockIdx.x * ZD_WARPS + warp) * ZD_LITBUF;
+	size_t gw = (size_t)blockIdx.x * ZD_WARPS + warp;
+	u64* arena = seq_arenas + gw * ZD_SEQ_ARENA;
+	u8* litbuf = litbufs + gw * ZD_LITBUF;
+	u32* my_slot = tabs + (gw * 32 + lane) * ZD_TAB_SLOT;
+	u8* hufsave0 = hufsaves + gw * 32 * ZD_HUFSAVE;
 	for (;;) {
-		u32 k = 0;
-		if (lane == 0) k = atomicAdd(queue, 1u);
-		k = __shfl_sync(ZG_FULL, k, 0);
-		if (k >= nframes) break;
-		u64 fo = off[k], fl = len[k], ul = ulen[k], oo = out_off[k];
-		u32 r;
-		u64 prod = 0;
-		u32 ck = 0;
-		bool has = false;
-		if (fo > archive_len || fl > archive_len - fo) r = ZS_E_SRC_SIZE;
-		else if (oo > out_cap || ul > out_cap - oo) r = ZS_E_DST_SMALL;
-		else r = zd_frame(W, archive + fo, fl, out + oo, ul, litbuf, &prod, &ck, &has);
-		__syncwarp();
-		if (lane == 0) {
-			status[k] = r;
-			produced[k] = prod;
-			cksums[2 * k] = ck;
-			cksums[2 * k + 1] = has ? 1u : 0u;
+		u32 base = 0;
+		if (lane == 0) base = atomicAdd(queue, 32u);
+		base = __shfl_sync(ZG_FULL, base, 0);
+		if (base >= nframes) break;
+		u64 k = (u64)base + lane;
+		bool mine = k < nframes;
+		// ---- lane-private frame header ----
+		ZdLane L;
+		L.src = archive;
+		L.out = out;
+		L.n = L.ip = L.cap = L.opos = L.fcs = 0;
+		L.status = ZS_OK;
+		L.flags = 0;
+		L.fcs_len = L.cksum = 0;
+		L.rep0 = 1;
+		L.rep1 = 4;
+		L.rep2 = 8;
+		L.ll_log = L.ml_log = L.of_log = 0;
+		L.blk = archive;
+		L.blk_n = L.nseq = L.nseq_left = L.seq_base = 0;
+		L.b.start = L.b.ptr = archive;
+		L.b.lo = L.b.hi = L.b.consumed = 0;
+		L.sl = L.so = L.sm = 0;
+		if (mine) {
+			u64 fo = off[k], fl = len[k], ul = ulen[k], oo = out_off[k];
+			if (fo > archive_len || fl > archive_len - fo) L.status = ZS_E_SRC_SIZE;
+			else if (oo > out_cap || ul > out_cap - oo) L.status = ZS_E_DST_SMALL;
+			else {
+				L.src = archive + fo;
+				L.n = fl;
+				L.out = out + oo;
+				L.cap = ul;
+				L.flags = ZD_F_ACTIVE;
+				zd_frame_header(L);
+			}
 		}
+		__syncwarp();
+		// ---- rounds: one block per live frame ----
+		for (;;) {
+			u32 live = __ballot_sync(ZG_FULL, (L.flags & ZD_F_ACTIVE) != 0);
+			if (!live) break;
+			// A: set up the next block of every live frame
+			u32 arena_used = 0;
+			u32 todo = live;
+			while (todo) {
+				int f = __ffs((int)todo) - 1;
+				todo &= todo - 1;
+				ZdLane U = zd_bcast(L, f);
+				zd_setup_frame(W, U, tabs + (gw * 32 + (u32)f) * ZD_TAB_SLOT, arena_used, litbuf, hufsave0 + (u32)f * ZD_HUFSAVE);
+				if (lane == (u32)f) L = U;
+				__syncwarp();
+			}
+			// B: every lane decodes its block's sequences (in bounded steps, so the warp reconverges)
+			{
+				const u32* llt = (L.flags & ZD_F_LL_DEF) ? ZS_LL_DEFAULT_DTABLE : my_slot;
+				const u32* mlt = (L.flags & ZD_F_ML_DEF) ? ZS_ML_DEFAULT_DTABLE : my_slot + 512;
+				const u32* oft = (L.flags & ZD_F_OF_DEF) ? ZS_OF_DEFAULT_DTABLE : my_slot + 1024;
+				for (;;) {
+					u32 cnt = zg_min<u32>(64u, L.nseq_left);
+					if (!__any_sync(ZG_FULL, cnt > 0)) break;
+					if (cnt && !zd_lane_decode(L, cnt, llt, mlt, oft, arena + L.seq_base + (L.nseq - L.nseq_left))) zd_fail(L, ZS_E_CORRUPT);
+				}
+			}
+			__syncwarp();
+			// C: execute frame after frame
+			todo = __ballot_sync(ZG_FULL, (L.flags & ZD_F_ACTIVE) && L.nseq > 0);
+			while (todo) {
+				int f = __ffs((int)todo) - 1;
+				todo &= todo - 1;
+				ZdLane U = zd_bcast(L, f);
+				zd_exec_block(W, U, arena + U.seq_base, litbuf, hufsave0 + (u32)f * ZD_HUFSAVE);
+				if (lane == (u32)f) L = U;
+				__syncwarp();
+			}
+		}
+		if (mine) {
+			bool ok = L.status == ZS_OK;
+			status[k] = L.status;
+			produced[k] = ok ? L.opos : 0;
+			cksums[2 * k] = ok ? L.cksum : 0;
+			cksums[2 * k + 1] = (ok && (L.flags & ZD_F_HAS_CK)) ? 1u : 0u;
+		}
+		__syncwarp();
 	}
 }
 
@@ -681,12 +933,23 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
                           const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,
                           u32* cksums) {
 	if (n == 0) return 0;
-	u32 grid = (u32)zg_min<u64>((n + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * 5);
-	if (w.lit.reserve((size_t)grid * ZD_WARPS * ZD_LITBUF) || w.queue.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
+	u64 batches = (n + 31) / 32;
+	u32 grid = (u32)zg_min<u64>((batches + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * 4);
+	size_t warps = (size_t)grid * ZD_WARPS;
+	if (w.seqs.reserve(warps * ZD_SEQ_ARENA * 8) || w.lit.reserve(warps * ZD_LITBUF) || w.tabs.reserve(warps * 32 * ZD_TAB_SLOT * 4) ||
+	    w.hufsave.reserve(warps * 32 * ZD_HUFSAVE) || w.queue.reserve(16))
+		return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.queue.p, 0, 16, s);
+	size_t smem = sizeof(ZdWarp) * ZD_WARPS;
+	static bool attr_set = false;
+	if (!attr_set) {
+		if (cudaFuncSetAttribute(k_zstd_decode_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+			return ZG_ERR(ZG_error_device);
+		attr_set = true;
+	}
 	zg_prof_begin(ZG_K_DECODE, s);
-	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, 0, s, archive, archive_len, off, len, ulen, out_off, n, out, out_cap,
-	          w.lit.as<u8>(), w.queue.as<u32>(), status, produced, cksums);
+	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, smem, s, archive, archive_len, off, len, ulen, out_off, n, out, out_cap,
+	          w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums);
 	zg_prof_end(ZG_K_DECODE, s);
 	ZG_COUNT_LAUNCH();
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
