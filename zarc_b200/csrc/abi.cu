@@ -308,6 +308,8 @@ void zg_dctx_free(zg_dctx* d) {
 	if (!d) return;
 	cudaStreamSynchronize(d->stream);
 	d->zd.lit.release();
+	d->zd.bins.release();
+	d->zd.perm.release();
 	d->zd.seqs.release();
 	d->zd.tabs.release();
 	d->zd.hufsave.release();

@@ -81,6 +81,7 @@ struct ZgZdWork {
 	ZgBuf tabs;     // per-lane FSE decode-table slots
 	ZgBuf hufsave;  // per-lane Huffman weights (Treeless blocks)
 	ZgBuf queue;    // frame queue counter
+	ZgBuf bins, perm;  // size-sorted frame order
 };
 size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
                           const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,

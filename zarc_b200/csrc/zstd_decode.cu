@@ -26,6 +26,7 @@
 #include "zstd_common.cuh"
 
 #define ZD_WARPS 4
+#define ZD_MIN_CTAS 5                    // occupancy target: 20 warps / SM
 #define ZD_SEQ_ARENA (1u << 17)          // u64 entries of sequence staging per warp (1 MiB)
 #define ZD_LITBUF (ZS_BLOCK_MAX + 64)    // bytes of literal staging per warp
 #define ZD_TAB_SLOT 1280u                // u32 entries per lane: LL 512 | ML 512 | OF 256
@@ -830,10 +831,49 @@ ZG_DEV void zd_exec_block(ZdWarp* W, ZdLane& U, const u64* seqs, u8* litbuf, u8*
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ZD_WARPS * 32)
+// Frames are handed to the warps in descending order of compressed size (counting sort), so that the
+// 32 frames of a batch carry similar numbers of sequences (phase B runs in lock-step) and the big
+// frames start first.
+#define ZD_BINS 4096u
+ZG_DEV u32 zd_bin(u64 len) { return ZD_BINS - 1u - (u32)zg_min<u64>(len >> 4, ZD_BINS - 1u); }
+__global__ void __launch_bounds__(256) k_zd_bin_count(const u64* __restrict__ len, u64 n, u32* bins) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) atomicAdd(&bins[zd_bin(len[k])], 1u);
+}
+__global__ void __launch_bounds__(1024) k_zd_bin_scan(u32* bins) {
+	// exclusive scan of ZD_BINS counters by one CTA (4 per thread)
+	__shared__ u32 part[32];
+	u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
+	u32 v[4], sum = 0;
+	for (u32 i = 0; i < 4; i++) {
+		v[i] = bins[4 * t + i];
+		sum += v[i];
+	}
+	u32 incl = zg_warp_incl_scan(sum);
+	if (lane == 31) part[w] = incl;
+	__syncthreads();
+	if (w == 0) {
+		u32 p = part[lane];
+		u32 pi = zg_warp_incl_scan(p);
+		part[lane] = pi - p;
+	}
+	__syncthreads();
+	u32 run = part[w] + incl - sum;
+	for (u32 i = 0; i < 4; i++) {
+		bins[4 * t + i] = run;
+		run += v[i];
+	}
+}
+__global__ void __launch_bounds__(256) k_zd_bin_scatter(const u64* __restrict__ len, u64 n, u32* bins, u32* perm) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) perm[atomicAdd(&bins[zd_bin(len[k])], 1u)] = (u32)k;
+}
+
+__global__ void __launch_bounds__(ZD_WARPS * 32, ZD_MIN_CTAS)
 k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
                      const u64* __restrict__ ulen, const u64* __restrict__ out_off, u64 nframes, u8* out, u64 out_cap,
-                     u64* seq_arenas, u8* litbufs, u32* tabs, u8* hufsaves, u32* queue, u32* status, u64* produced, u32* cksums) {
+                     const u32* __restrict__ perm, u64* seq_arenas, u8* litbufs, u32* tabs, u8* hufsaves, u32* queue, u32* status,
+                     u64* produced, u32* cksums) {
 	ZG_DYN_SMEM(ZdWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZdWarp* W = &sm[warp];
@@ -847,8 +887,8 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 		if (lane == 0) base = atomicAdd(queue, 32u);
 		base = __shfl_sync(ZG_FULL, base, 0);
 		if (base >= nframes) break;
-		u64 k = (u64)base + lane;
-		bool mine = k < nframes;
+		bool mine = (u64)base + lane < nframes;
+		u64 k = mine ? (perm ? (u64)perm[base + lane] : (u64)base + lane) : 0;
 		// ---- lane-private frame header ----
 		ZdLane L;
 		L.src = archive;
@@ -934,12 +974,25 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
                           u32* cksums) {
 	if (n == 0) return 0;
 	u64 batches = (n + 31) / 32;
-	u32 grid = (u32)zg_min<u64>((batches + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * 4);
+	u32 grid = (u32)zg_min<u64>((batches + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * ZD_MIN_CTAS);
 	size_t warps = (size_t)grid * ZD_WARPS;
 	if (w.seqs.reserve(warps * ZD_SEQ_ARENA * 8) || w.lit.reserve(warps * ZD_LITBUF) || w.tabs.reserve(warps * 32 * ZD_TAB_SLOT * 4) ||
-	    w.hufsave.reserve(warps * 32 * ZD_HUFSAVE) || w.queue.reserve(16))
+	    w.hufsave.reserve(warps * 32 * ZD_HUFSAVE) || w.queue.reserve(16) || w.bins.reserve(ZD_BINS * 4) || w.perm.reserve(n * 4))
 		return ZG_ERR(ZG_error_memory_allocation);
+	if (n >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
 	cudaMemsetAsync(w.queue.p, 0, 16, s);
+	const u32* perm = nullptr;
+	if (n > 64) {
+		cudaMemsetAsync(w.bins.p, 0, ZD_BINS * 4, s);
+		u32 g = (u32)((n + 255) / 256);
+		ZG_LAUNCH(k_zd_bin_count, g, 256, 0, s, len, n, w.bins.as<u32>());
+		ZG_LAUNCH(k_zd_bin_scan, 1, 1024, 0, s, w.bins.as<u32>());
+		ZG_LAUNCH(k_zd_bin_scatter, g, 256, 0, s, len, n, w.bins.as<u32>(), w.perm.as<u32>());
+		ZG_COUNT_LAUNCH();
+		ZG_COUNT_LAUNCH();
+		ZG_COUNT_LAUNCH();
+		perm = w.perm.as<u32>();
+	}
 	size_t smem = sizeof(ZdWarp) * ZD_WARPS;
 	static bool attr_set = false;
 	if (!attr_set) {
@@ -949,7 +1002,7 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 	}
 	zg_prof_begin(ZG_K_DECODE, s);
 	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, smem, s, archive, archive_len, off, len, ulen, out_off, n, out, out_cap,
-	          w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums);
+	          perm, w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums);
 	zg_prof_end(ZG_K_DECODE, s);
 	ZG_COUNT_LAUNCH();
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
