@@ -30,10 +30,13 @@ ZG_DEV u32 ze_ll_code(u32 ll) { return ll < 64 ? ZS_LL_CODE[ll] : zs_highbit(ll)
 ZG_DEV u32 ze_ml_code(u32 mlbase) { return mlbase < 128 ? ZS_ML_CODE[mlbase] : zs_highbit(mlbase) + 36; }
 
 // per-warp global scratch
+// seq: offset-or-offBase (17 bits) | litLength << 17 (17 bits) | matchLength << 34
+#define ZE_SEQ_OF(q) ((u32)(q) & 0x1ffffu)
+#define ZE_SEQ_LL(q) ((u32)((q) >> 17) & 0x1ffffu)
+#define ZE_SEQ_ML(q) ((u32)((q) >> 34))
+#define ZE_SEQ_PACK(of, ll, ml) ((u64)(of) | ((u64)(ll) << 17) | ((u64)(ml) << 34))
 struct ZeScratch {
-	u32 ll[ZE_MAXSEQ];
-	u32 ml[ZE_MAXSEQ];
-	u32 ofb[ZE_MAXSEQ];   // offBase: 1..3 repeat codes, else offset + 3
+	u64 seq[ZE_MAXSEQ];
 	u32 codes[ZE_MAXSEQ]; // ll | ml << 8 | of << 16
 	u16 stb[3][ZE_MAXSEQ]; // per sequence, per table (LL, ML, OF): FSE state bits value | nbBits << 12
 	u8 lit[ZS_BLOCK_MAX + 64];
@@ -591,17 +594,19 @@ ZG_DEV u32 ze_seq_table(ZeEnt& e, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: match finding over one block.  Returns nseq; *lit_count = literals gathered into S->lit,
-// with the trailing literals (after the last match) included.
-struct ZeRep {
-	u32 r0, r1, r2;
-	u32 known;  // how many of r0,r1,r2 the decoder is known to hold (3 at frame start)
-};
-
+// K2: match finding over one block.  Returns nseq; *lit_count = literals gathered into S->lit (the
+// literals after the last match included).  Sequences land in S->seq with their plain offsets; the
+// repeat-offset codes are assigned afterwards by ze_assign_repcodes.
+//
+// Per window of 32 positions: every lane looks up, verifies and extends its own candidate; a short
+// warp-uniform loop only SELECTS the matches (greedy, one-step lazy); everything per sequence --
+// literal length, the sequence record, gathering the uncovered bytes into the literal buffer and
+// histogramming them -- is then done lane-parallel from the selection mask.
 ZG_DEV u32 ze_hash4(u32 v, u32 hlog) { return (v * 2654435761u) >> (32 - hlog); }
 
-ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, ZeRep rep, u32 lazy, u32* lit_count) {
+ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 lazy, u32* lit_count) {
 	u32 lane = zg_lane();
+	u32 ltmask = zg_lanemask_lt();
 	u32 hlog = 8;
 	while (hlog < ZE_HLOG_MAX && (1u << hlog) < n) hlog++;
 	u16* htab = W->u.htab;
@@ -611,20 +616,23 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, ZeRep r
 		for (u32 i = lane; i < 256; i += 32) W->hist[i] = 0;
 	}
 	__syncwarp();
-	u32 anchor = 0, lpos = 0, nseq = 0, ip = 0;
-	while (ip + ZE_MINMATCH <= n && nseq < ZE_MAXSEQ - 1) {
+	u32 mend = 0;      // end of the last match = start of the pending literals
+	u32 last_off = 0;  // its offset
+	u32 lpos = 0, nseq = 0, ip = 0;
+	while (ip < n && nseq < ZE_MAXSEQ - 32) {
 		u32 pos = ip + lane;
+		bool inb = pos < n;
 		bool valid = pos + 4 <= n;
-		u32 v = valid ? zg_ld32(src + pos) : 0;
+		u32 v = valid ? zg_ld32(src + pos) : (inb ? (u32)src[pos] : 0u);
 		u32 h = valid ? ze_hash4(v, hlog) : (0x80000000u | lane);
 		u32 te = valid ? htab[h] : 0;
 		u32 peers = __match_any_sync(ZG_FULL, h);
 		__syncwarp();
 		if (valid && (peers >> lane) == 1u) htab[h] = (u16)pos;  // highest lane of each hash group
 		// candidate: nearest earlier lane with the same hash, else the table entry
-		u32 lower = peers & zg_lanemask_lt();
+		u32 lower = peers & ltmask;
 		i32 cand = -1;
-		if (valid) {
+		if (valid && pos >= mend) {
 			if (lower) {
 				cand = (i32)(ip + (31u - (u32)__clz((int)lower)));
 			} else {
@@ -650,10 +658,11 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, ZeRep r
 		}
 		u32 moff = mlen ? pos - (u32)cand : 0;
 		__syncwarp();
-		// ---- warp-uniform parse of this window ----
+		// ---- selection (warp-uniform, as little as possible) ----
 		u32 has = __ballot_sync(ZG_FULL, mlen >= ZE_MINMATCH);
-		u32 cur = ip;
-		while (has && nseq < ZE_MAXSEQ - 1) {
+		u32 sel = 0;
+		u32 cur = mend;
+		while (has) {
 			u32 i = (u32)__ffs((int)has) - 1;
 			u32 L = __shfl_sync(ZG_FULL, mlen, (int)i), O = __shfl_sync(ZG_FULL, moff, (int)i);
 			if (lazy && i < 31 && ((has >> (i + 1)) & 1)) {
@@ -664,6 +673,13 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, ZeRep r
 				}
 			}
 			u32 p = ip + i;
+			if (p == cur && O == last_off && (nseq | sel)) {
+				// would continue the previous match with a zero literal length and the same offset: the
+				// repeat-offset model below relies on this never being emitted (maximal matches make it
+				// impossible in practice)
+				has &= ~(1u << i);
+				continue;
+			}
 			if (L >= ZE_LANE_CAP && p + L < n) {
 				// whole-warp extension, 128 bytes per step
 				for (;;) {
@@ -684,75 +700,135 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, ZeRep r
 					L += 4 * first + __shfl_sync(ZG_FULL, eq, (int)first);
 					break;
 				}
+				if (lane == i) mlen = L;
 			}
-			u32 ll = p - anchor;
-			// literals of this sequence -> S->lit, histogram
-			for (u32 k = lane; k < ll; k += 32) {
-				u32 b = src[anchor + k];
-				S->lit[lpos + k] = (u8)b;
-				atomicAdd(&W->hist[b], 1u);
-			}
-			// repeat-offset codes (RFC 8878 §3.1.1.5), tracking which history slots are known
-			u32 ofb;
-			if (ll > 0) {
-				if (rep.known >= 1 && O == rep.r0) ofb = 1;
-				else if (rep.known >= 2 && O == rep.r1) ofb = 2;
-				else if (rep.known >= 3 && O == rep.r2) ofb = 3;
-				else ofb = O + 3;
-			} else {
-				if (rep.known >= 2 && O == rep.r1) ofb = 1;
-				else if (rep.known >= 3 && O == rep.r2) ofb = 2;
-				else if (rep.known >= 1 && rep.r0 > 1 && O == rep.r0 - 1) ofb = 3;
-				else ofb = O + 3;
-			}
-			if (ofb > 3) {
-				rep.r2 = rep.r1;
-				rep.r1 = rep.r0;
-				rep.r0 = O;
-				if (rep.known < 3) rep.known++;
-			} else {
-				u32 idx = ofb - 1 + (ll == 0 ? 1 : 0);
-				if (idx == 1) {
-					u32 t = rep.r1;
-					rep.r1 = rep.r0;
-					rep.r0 = t;
-				} else if (idx == 2) {
-					u32 t = rep.r2;
-					rep.r2 = rep.r1;
-					rep.r1 = rep.r0;
-					rep.r0 = t;
-				} else if (idx == 3) {
-					rep.r2 = rep.r1;
-					rep.r1 = rep.r0;
-					rep.r0 = O;
-					// r0-1 pushed: slots shift down, still as many known as before (at least 1)
-				}
-			}
-			if (lane == 0) {
-				S->ll[nseq] = ll;
-				S->ml[nseq] = L;
-				S->ofb[nseq] = ofb;
-			}
-			nseq++;
-			lpos += ll;
-			anchor = p + L;
-			cur = anchor;
+			sel |= 1u << i;
+			last_off = O;
+			cur = p + L;
 			u32 rel = cur - ip;
 			has = rel >= 32 ? 0 : (has & ~((1u << rel) - 1u));
 		}
+		// ---- emission (lane-parallel) ----
+		u32 below = sel & ltmask;
+		u32 my_end = pos + mlen;
+		u32 pend = __shfl_sync(ZG_FULL, my_end, below ? (int)(31u - (u32)__clz((int)below)) : 0);
+		u32 prev_end = below ? pend : mend;  // end of the nearest match that starts before this position
+		bool selme = (sel >> lane) & 1u;
+		if (selme) S->seq[nseq + (u32)__popc(below)] = ZE_SEQ_PACK(moff, pos - prev_end, mlen);
+		bool is_lit = inb && !selme && pos >= prev_end;
+		u32 lm = __ballot_sync(ZG_FULL, is_lit);
+		if (is_lit) {
+			u32 b = v & 0xffu;
+			S->lit[lpos + (u32)__popc(lm & ltmask)] = (u8)b;
+			atomicAdd(&W->hist[b], 1u);
+		}
+		lpos += (u32)__popc(lm);
+		nseq += (u32)__popc(sel);
+		mend = cur;
 		ip = zg_max<u32>(ip + 32, cur);
 	}
-	// trailing literals
-	u32 rest = n - anchor;
-	for (u32 k = lane; k < rest; k += 32) {
-		u32 b = src[anchor + k];
-		S->lit[lpos + k] = (u8)b;
-		atomicAdd(&W->hist[b], 1u);
+	// the rest (only when the sequence budget ran out)
+	{
+		u32 start = zg_max<u32>(ip, mend);
+		u32 rest = start < n ? n - start : 0;
+		for (u32 k = lane; k < rest; k += 32) {
+			u32 b = src[start + k];
+			S->lit[lpos + k] = (u8)b;
+			atomicAdd(&W->hist[b], 1u);
+		}
+		lpos += rest;
 	}
-	lpos += rest;
 	__syncwarp();
 	*lit_count = lpos;
 	return nseq;
+}
+
+// Repeat-offset codes (RFC 8878 §3.1.1.5) for all sequences of the block, 32 at a time.
+// The decoder's history is a move-to-front list of the three most recently used distinct offsets
+// (the parse never emits "zero literals + the offset just used", the one transition that is not
+// MTF), so for sequence j: rep0 = the previous sequence's offset, rep1 = the last offset different
+// from it (found exactly, by a segmented scan), rep2 = the last one different from both (bounded
+// look-back; not finding it only costs a code, the decoder's state is the same either way).
+// History slots a block cannot know (blocks after the first are encoded independently) are 0 and
+// never match.  Rewrites S->seq[i].of from offset to offBase.  Returns false if the impossible
+// transition is met (the caller then stores the block raw).
+#define ZE_REP_LOOKBACK 8u
+ZG_DEV bool ze_assign_repcodes(ZeWarp* W, ZeScratch* S, u32 nseq, bool first_block) {
+	u32 lane = zg_lane();
+	u32* ro = W->u.e.window;  // [ZE_REP_LOOKBACK + 32] offsets: the previous chunk's tail, then this chunk
+	if (lane < ZE_REP_LOOKBACK) ro[lane] = 0;
+	__syncwarp();
+	u32 a_carry = 0, b_carry = 0;
+	if (first_block) {
+		if (lane == 0) {
+			ro[ZE_REP_LOOKBACK - 1] = 1;
+			ro[ZE_REP_LOOKBACK - 2] = 4;
+			ro[ZE_REP_LOOKBACK - 3] = 8;
+		}
+		a_carry = 1;
+		b_carry = 4;
+	}
+	__syncwarp();
+	bool ok = true;
+	for (u32 s0 = 0; s0 < nseq; s0 += 32) {
+		u32 cnt = zg_min<u32>(32u, nseq - s0);
+		bool act = lane < cnt;
+		u64 q = act ? S->seq[s0 + lane] : 0;
+		u32 O = ZE_SEQ_OF(q), ll = ZE_SEQ_LL(q);
+		u32 olast = __shfl_sync(ZG_FULL, O, (int)cnt - 1);
+		if (!act) O = olast;  // idle lanes repeat the last offset: no change points
+		ro[ZE_REP_LOOKBACK + lane] = O;
+		u32 prevO = __shfl_up_sync(ZG_FULL, O, 1);
+		if (lane == 0) prevO = a_carry;
+		// rep1 AFTER sequence j: the offset before the last change point at or before j
+		i32 chg = (O != prevO) ? (i32)lane : -1;
+		for (int d = 1; d < 32; d <<= 1) {
+			i32 t = __shfl_up_sync(ZG_FULL, chg, d);
+			if ((int)lane >= d) chg = chg > t ? chg : t;
+		}
+		u32 b_after = __shfl_sync(ZG_FULL, prevO, chg < 0 ? 0 : chg);
+		if (chg < 0) b_after = b_carry;
+		u32 a = prevO;
+		u32 b = __shfl_up_sync(ZG_FULL, b_after, 1);
+		if (lane == 0) b = b_carry;
+		__syncwarp();
+		u32 c = 0;
+		for (u32 k = 2; k < 2 + ZE_REP_LOOKBACK - 1; k++) {
+			// offsets of sequences j-2, j-3, ... (index ZE_REP_LOOKBACK + lane - k in the ring)
+			u32 idx = ZE_REP_LOOKBACK + lane - k;
+			if (idx > ZE_REP_LOOKBACK + 31) break;  // (unsigned wrap) beyond the ring
+			u32 x = ro[idx];
+			if (x == 0) break;
+			if (x != a && x != b) {
+				c = x;
+				break;
+			}
+		}
+		u32 ofb;
+		if (ll > 0) {
+			if (O == a) ofb = 1;
+			else if (O == b) ofb = 2;
+			else if (O == c) ofb = 3;
+			else ofb = O + 3;
+		} else {
+			if (O == a) {
+				ok = ok && !act;
+				ofb = O + 3;
+			} else if (O == b) ofb = 1;
+			else if (O == c) ofb = 2;
+			else if (a > 1 && O == a - 1) ofb = 3;
+			else ofb = O + 3;
+		}
+		if (act) S->seq[s0 + lane] = ZE_SEQ_PACK(ofb, ll, ZE_SEQ_ML(q));
+		a_carry = __shfl_sync(ZG_FULL, O, 31);
+		b_carry = __shfl_sync(ZG_FULL, b_after, 31);
+		__syncwarp();
+		u32 keep = lane < ZE_REP_LOOKBACK ? ro[32 + lane] : 0;
+		__syncwarp();
+		if (lane < ZE_REP_LOOKBACK) ro[lane] = keep;
+		__syncwarp();
+	}
+	return __all_sync(ZG_FULL, ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -894,7 +970,8 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZeScratch* S, u32 nseq, u32 nlit, u8* dst
 	__syncwarp();
 	u32 mx_ll = 0, mx_ml = 0, mx_of = 0;
 	for (u32 i = lane; i < nseq; i += 32) {
-		u32 lc = ze_ll_code(S->ll[i]), mc = ze_ml_code(S->ml[i] - 3), oc = zs_highbit(S->ofb[i]);
+		u64 q = S->seq[i];
+		u32 lc = ze_ll_code(ZE_SEQ_LL(q)), mc = ze_ml_code(ZE_SEQ_ML(q) - 3), oc = zs_highbit(ZE_SEQ_OF(q));
 		S->codes[i] = lc | (mc << 8) | (oc << 16);
 		atomicAdd(&e.hist3[0][lc], 1u);
 		atomicAdd(&e.hist3[1][mc], 1u);
@@ -963,11 +1040,12 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZeScratch* S, u32 nseq, u32 nlit, u8* dst
 			nb += b >> 12;
 			lo64 |= (u64)(d & 0xfff) << nb;
 			nb += d >> 12;
-			lo64 |= (u64)(S->ll[i] - ZS_LL_BASE[lc]) << nb;
+			u64 q = S->seq[i];
+			lo64 |= (u64)(ZE_SEQ_LL(q) - ZS_LL_BASE[lc]) << nb;
 			nb += ZS_LL_BITS[lc];
-			lo64 |= (u64)(S->ml[i] - ZS_ML_BASE[mc]) << nb;
+			lo64 |= (u64)(ZE_SEQ_ML(q) - ZS_ML_BASE[mc]) << nb;
 			nb += ZS_ML_BITS[mc];  // <= 58 bits so far
-			u64 ox = S->ofb[i] - (1u << oc);
+			u64 ox = ZE_SEQ_OF(q) - (1u << oc);
 			lo64 |= ox << nb;
 			if (nb + oc > 64) hi32 = (u32)(ox >> (64 - nb));
 			nb += oc;
@@ -1030,15 +1108,13 @@ k_zstd_encode_blocks(const u8* __restrict__ blob, const u64* __restrict__ file_o
 		u8* dst = comp + comp_off[f] + boff;
 		u32 csize = 0;
 		if (n >= 16) {
-			ZeRep rep;
-			rep.r0 = 1;
-			rep.r1 = 4;
-			rep.r2 = 8;
-			rep.known = j == 0 ? 3 : 0;  // later blocks are encoded independently of their predecessors
 			u32 nlit = 0;
-			u32 nseq = ze_match_block(W, S, src, n, rep, prm.lazy, &nlit);
+			u32 nseq = ze_match_block(W, S, src, n, prm.lazy, &nlit);
 			__syncwarp();
-			csize = ze_entropy_block(W, S, nseq, nlit, dst, n - 1);
+			// later blocks of a frame are encoded independently of their predecessors: unknown history
+			if (ze_assign_repcodes(W, S, nseq, j == 0))
+				csize = ze_entropy_block(W, S, nseq, nlit, dst, n - 1);
+			__syncwarp();
 		}
 		__syncwarp();
 		if (lane == 0) blk_csize[b] = csize ? csize : (ZE_RAW | n);
