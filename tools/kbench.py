@@ -137,7 +137,15 @@ def main():
             lib.check(lib.zg_pack_batch_dev(cctx, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, d_dig.data_ptr(), d_first.data_ptr(),
                                             d_foff.data_ptr(), d_flen.data_ptr(), d_frames.data_ptr(), cap, nbytes.ctypes.data))
 
+        lib.zg_profile_enable(1)
         best, med = timeit(run_pack, iters=3, warmup=1)
+        lib.zg_profile_enable(0)
+        import ctypes as C
+        for k, name in enumerate(["blake3", "encode", "decode", "assemble", "xxh64", "dedup"]):
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            lib.zg_profile_read(k, C.byref(ms), C.byref(cnt))
+            if cnt.value:
+                res[f"ms_{name}"] = round(ms.value / cnt.value, 3)
         res[f"pack_c2_L{args.level}_gbs"] = c.total_bytes / best / 1e6
         res["pack_ratio"] = c.total_bytes / float(nbytes[0])
         res["pack_unique"] = int(d_first.sum())

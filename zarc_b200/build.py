@@ -50,7 +50,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     for src in _sources():
         o = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-c", src, "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("ZG_NVCC_EXTRA", "").split(), "-I", CSRC, "-c", src, "-o", o]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
@@ -63,7 +63,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-shared", "-o", PRODUCT_SO, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", PRODUCT_SO, *objs, "-lcudart"])
     return PRODUCT_SO
 
 

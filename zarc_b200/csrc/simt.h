@@ -15,15 +15,24 @@ static inline void zg_emu_launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t s
 	zg_emu_launch_k(kernel, dim3(grid), dim3(block), (smem), __VA_ARGS__)
 #define ZG_UNROLL
 #define ZG_CONST_TABLE static const
+#define zg_prefetch_l2(p) ((void)(p))
 #else
 #include <cuda_runtime.h>
 #define ZG_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; type* name = (type*)name##_raw_
 #define ZG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define ZG_UNROLL _Pragma("unroll")
 #define ZG_CONST_TABLE static __device__ const
+#define zg_prefetch_l2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
 #define ZG_DEV __device__ __forceinline__
+#ifdef ZG_EMU
+#define ZG_DEV_NOINLINE static __attribute__((noinline))
+#define ZG_UNROLL1
+#else
+#define ZG_DEV_NOINLINE static __device__ __noinline__
+#define ZG_UNROLL1 _Pragma("unroll 1")
+#endif
 #define ZG_HD __host__ __device__ __forceinline__
 #define ZG_FULL 0xffffffffu
 

@@ -17,7 +17,12 @@
 #include "zstd_common.cuh"
 
 #define ZE_WARPS 4
+#ifndef ZE_HLOG_MAX
 #define ZE_HLOG_MAX 13
+#endif
+#ifndef ZE_MIN_CTAS
+#define ZE_MIN_CTAS 3
+#endif
 #define ZE_MAXSEQ 32768u
 #define ZE_MINMATCH 4u
 #define ZE_LANE_CAP 64u   // per-lane match extension cap; longer matches are extended by the whole warp
@@ -45,15 +50,21 @@ struct ZeScratch {
 struct ZeEnt {
 	u16 hcode[256];       // Huffman code | nbBits << 11
 	u8 hweight[256];
-	u16 sorted_sym[256];
-	u32 sorted_cnt[256];
-	u32 node_cnt[512];
-	u16 node_par[512];
-	u8 node_depth[512];
-	u16 st[3][512];       // FSE state tables: LL, ML, OF (OF also serves the Huffman-weight table)
-	u32 dnb[3][64];       // symbolTT.deltaNbBits
-	i32 dfs[3][64];       // symbolTT.deltaFindState
-	u32 hist3[3][64];
+	union {               // the Huffman tree build is over before any FSE table exists
+		struct {
+			u16 sorted_sym[256];
+			u32 sorted_cnt[256];
+			u32 node_cnt[512];
+			u16 node_par[512];
+			u8 node_depth[512];
+		};
+		struct {
+			u16 st[3][512];   // FSE state tables: LL, ML, OF (OF also serves the Huffman-weight table)
+			u32 dnb[3][64];   // symbolTT.deltaNbBits
+			i32 dfs[3][64];   // symbolTT.deltaFindState
+			u32 hist3[3][64];
+		};
+	};
 	i16 norm[64];
 	u16 cumul[66];
 	u8 tsym[512];
@@ -85,7 +96,8 @@ ZG_DEV void ze_bw_init(ZeBitW& w, u8* p, u8* end) {
 	w.nbits = 0;
 	w.ovf = false;
 }
-ZG_DEV void ze_bw_flush(ZeBitW& w) {
+ZG_DEV_NOINLINE void ze_bw_flush(ZeBitW& w) {
+	ZG_UNROLL1
 	while (w.nbits >= 8) {
 		if (w.p < w.end) *w.p++ = (u8)w.acc;
 		else w.ovf = true;
@@ -132,7 +144,7 @@ ZG_DEV void ze_fse_encode(ZeBitW& w, const ZeCT& ct, u32& state, u32 sym) {
 ZG_DEV void ze_fse_flush_state(ZeBitW& w, const ZeCT& ct, u32 state) { ze_bw_add(w, state, ct.log); }
 
 // single lane.  norm may hold -1 ("less than one") entries: only the predefined tables do.
-ZG_DEV void ze_fse_build_ctable(const ZeCT& ct, const i16* norm, u32 maxsym, u8* tsym, u16* cumul) {
+ZG_DEV_NOINLINE void ze_fse_build_ctable(const ZeCT& ct, const i16* norm, u32 maxsym, u8* tsym, u16* cumul) {
 	u32 log = ct.log, size = 1u << log;
 	u32 high = size - 1;
 	cumul[0] = 0;
@@ -188,7 +200,7 @@ ZG_DEV u32 ze_fse_table_log(u32 maxlog, u32 total, u32 maxsym) {
 	return log;
 }
 // counts -> normalized counts summing to 2^log, every present symbol >= 1.  Single lane.
-ZG_DEV void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 maxsym, u32 log) {
+ZG_DEV_NOINLINE void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 maxsym, u32 log) {
 	u32 size = 1u << log;
 	i32 left = (i32)size;
 	u32 largest = 0, largest_p = 0;
@@ -198,9 +210,9 @@ ZG_DEV void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 maxsym, u
 			norm[s] = 0;
 			continue;
 		}
-		u64 scaled = ((u64)c << log);
-		u32 p = (u32)(scaled / total);
-		u32 rem = (u32)(scaled - (u64)p * total);
+		u32 scaled = c << log;  // <= 2^15 sequences (or 256 weights) << 9: fits 32 bits
+		u32 p = scaled / total;
+		u32 rem = scaled - p * total;
 		if (p == 0) p = 1;
 		else if (p < 8 && rem * 2 > total) p++;  // round small probabilities to nearest
 		if (p > largest_p) {
@@ -223,8 +235,98 @@ ZG_DEV void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 maxsym, u
 		left++;
 	}
 }
+// Warp-cooperative versions of the two functions above for the sequence tables (no -1 entries).
+// Same results as the single-lane code: libzstd's spread visits slot k of the cumulative order at
+// table position (k * step) & mask, and hands out each symbol's states in increasing table position.
+ZG_DEV_NOINLINE void ze_fse_build_ctable_warp(const ZeCT& ct, const i16* norm, u32 maxsym, u8* tsym, u16* cumul) {
+	u32 lane = zg_lane(), log = ct.log, size = 1u << log;
+	u32 s0 = 2 * lane, s1 = s0 + 1;
+	u32 n0 = s0 <= maxsym ? (u32)norm[s0] : 0u, n1 = s1 <= maxsym ? (u32)norm[s1] : 0u;
+	u32 incl = zg_warp_incl_scan(n0 + n1);
+	u32 ex0 = incl - n0 - n1, ex1 = ex0 + n0;
+	if (s0 <= maxsym + 1) cumul[s0] = (u16)ex0;
+	if (s1 <= maxsym + 1) cumul[s1] = (u16)ex1;
+	ZG_UNROLL
+	for (int k = 0; k < 2; k++) {
+		u32 s = k ? s1 : s0, n = k ? n1 : n0, ex = k ? ex1 : ex0;
+		if (s > maxsym) continue;
+		if (n == 0) {
+			ct.dnb[s] = ((log + 1) << 16) - size;
+			ct.dfs[s] = 0;
+		} else if (n == 1) {
+			ct.dnb[s] = (log << 16) - size;
+			ct.dfs[s] = (i32)ex - 1;
+		} else {
+			u32 maxbits = log - zs_highbit(n - 1);
+			ct.dnb[s] = (maxbits << 16) - (n << maxbits);
+			ct.dfs[s] = (i32)ex - (i32)n;
+		}
+	}
+	__syncwarp();
+	u32 step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+	for (u32 k = lane; k < size; k += 32) {
+		u32 s = 0;  // the symbol owning slot k: largest s with cumul[s] <= k
+		ZG_UNROLL
+		for (u32 b = 32; b; b >>= 1) {
+			u32 c = s + b;
+			if (c <= maxsym && cumul[c] <= k) s = c;
+		}
+		tsym[(k * step) & mask] = (u8)s;
+	}
+	__syncwarp();
+	for (u32 u0 = 0; u0 < size; u0 += 32) {  // size >= 32
+		u32 u = u0 + lane;
+		u32 sym = tsym[u];
+		u32 peers = __match_any_sync(ZG_FULL, sym);
+		u32 rank = (u32)__popc(peers & zg_lanemask_lt());
+		u32 base = cumul[sym];
+		__syncwarp();
+		if (rank == 0) cumul[sym] = (u16)(base + (u32)__popc(peers));
+		ct.st[base + rank] = (u16)(size + u);
+		__syncwarp();
+	}
+}
+ZG_DEV_NOINLINE void ze_fse_normalize_warp(i16* norm, const u32* cnt, u32 total, u32 maxsym, u32 log) {
+	u32 lane = zg_lane();
+	u32 size = 1u << log;
+	u32 sum = 0, best = 0;
+	ZG_UNROLL
+	for (int k = 0; k < 2; k++) {
+		u32 s = lane + 32 * k;
+		u32 c = s <= maxsym ? cnt[s] : 0u;
+		u32 p = 0;
+		if (c) {
+			u32 scaled = c << log;  // <= 2^15 sequences << 9: fits 32 bits
+			p = scaled / total;
+			u32 rem = scaled - p * total;
+			if (p == 0) p = 1;
+			else if (p < 8 && rem * 2 > total) p++;
+		}
+		sum += p;
+		best = zg_max<u32>(best, (p << 6) | (63u - s));  // largest p, lowest symbol on ties
+		if (s <= maxsym) norm[s] = (i16)p;
+	}
+	sum = zg_warp_sum(sum);
+	best = zg_warp_max(best);
+	__syncwarp();
+	i32 left = (i32)size - (i32)sum;
+	u32 largest = 63u - (best & 63u);
+	i32 lp = (i32)(best >> 6);
+	if (left >= 0 || -left < (lp >> 1)) {
+		if (lane == 0) norm[largest] = (i16)(lp + left);
+	} else if (lane == 0) {
+		while (left < 0) {  // rare: too many forced-to-1 symbols
+			u32 big = 0;
+			for (u32 s = 1; s <= maxsym; s++)
+				if (norm[s] > norm[big]) big = s;
+			norm[big]--;
+			left++;
+		}
+	}
+	__syncwarp();
+}
 // FSE table description (NCount) writer, inverse of zs_read_ncount.  Single lane.  Returns bytes (0 = no room).
-ZG_DEV u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 maxsym, u32 log) {
+ZG_DEV_NOINLINE u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 maxsym, u32 log) {
 	ZeBitW w;
 	ze_bw_init(w, dst, dst + cap);
 	ze_bw_add(w, log - 5, 4);
@@ -266,7 +368,7 @@ ZG_DEV u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 maxsym, u3
 // ---------------------------------------------------------------------------------------------
 // Huffman: code lengths (<= 11 bits) from the literal histogram.  Returns maxBits (0 = failure),
 // fills e.hweight[0..maxsym], e.hcode[], *maxsym_out.  All lanes call.
-ZG_DEV u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
+ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	ZeEnt& e = W->u.e;
 	u32 lane = zg_lane();
 	// present symbols, ascending symbol order -> node_cnt/node_par as (cnt, sym) staging
@@ -349,7 +451,7 @@ ZG_DEV u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 }
 
 // Huffman tree description into e.wdesc (single lane).  Returns its size, 0 if not representable.
-ZG_DEV u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
+ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 	ZeEnt& e = W->u.e;
 	u32 nw = maxsym;  // weights 0..maxsym-1 are explicit, the last is implied
 	u32 direct = nw <= 128 ? 1 + ((nw + 1) >> 1) : 0;
@@ -409,7 +511,7 @@ ZG_DEV u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 }
 
 // total code bits of lit[0..m)
-ZG_DEV u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
+ZG_DEV_NOINLINE u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
 	u32 bits = 0;
 	for (u32 i = zg_lane(); i < m; i += 32) bits += e.hcode[lit[i]] >> 11;
 	return zg_warp_sum(bits);
@@ -417,7 +519,7 @@ ZG_DEV u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
 
 // One Huffman stream for lit[0..m) into dst (exactly `nbytes` bytes, as computed from count_bits).
 // The last literal is written first (lowest bits); parallel bit packing through a shared window.
-ZG_DEV void ze_huf_encode_stream(ZeWarp* W, const u8* lit, u32 m, u8* dst, u32 total_bits) {
+ZG_DEV_NOINLINE void ze_huf_encode_stream(ZeWarp* W, const u8* lit, u32 m, u8* dst, u32 total_bits) {
 	ZeEnt& e = W->u.e;
 	u32 lane = zg_lane();
 	u32* win = e.window;  // 96 words
@@ -552,44 +654,52 @@ ZG_DEV u32 ze_pack_finish(ZePack& P) {
 
 // ---------------------------------------------------------------------------------------------
 // sequence tables: mode choice (libzstd's heuristic for fast strategies), description, CTable.
-// Single lane.  Writes the description at *pp (bounded by end).  Returns mode, or 0xff on overflow.
-ZG_DEV u32 ze_seq_table(ZeEnt& e, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u32 maxlog, u32 deflog, const i16* defnorm,
-                        u32 defmax, u8*& p, u8* end, ZeCT& ct) {
-	u32 most = 0, most_sym = 0;
-	for (u32 s = 0; s <= maxsym; s++)
-		if (cnt[s] > most) {
-			most = cnt[s];
-			most_sym = s;
-		}
+// All lanes call.  Writes the description at p (bounded by end).  Returns mode, or 0xff on overflow.
+// The predefined tables are built once per CTA (ZePredef); only FSE_Compressed tables are built here.
+struct ZePredef {
+	u16 st_ll[64], st_ml[64], st_of[32];
+	u32 dnb_ll[36], dnb_ml[53], dnb_of[29];
+	i32 dfs_ll[36], dfs_ml[53], dfs_of[29];
+};
+ZG_DEV_NOINLINE u32 ze_seq_table(ZeWarp* W, const ZeCT& predef, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u32 maxlog, u32 defmax, u8*& p,
+                        u8* end, ZeCT& ct) {
+	ZeEnt& e = W->u.e;
+	u32 lane = zg_lane();
+	u32 c0 = lane <= maxsym ? cnt[lane] : 0u, c1 = lane + 32 <= maxsym ? cnt[lane + 32] : 0u;
+	u32 key = zg_warp_max(zg_max<u32>((c0 << 6) | (63u - lane), (c1 << 6) | (31u - lane)));
+	u32 most = key >> 6, most_sym = 63u - (key & 63u);
 	ct.st = e.st[t];
 	ct.dnb = e.dnb[t];
 	ct.dfs = e.dfs[t];
 	if (most == nseq && nseq > 2) {  // RLE_Mode
 		if (p >= end) return 0xff;
-		*p++ = (u8)most_sym;
-		ct.log = 0;
-		ct.st[0] = 1;  // a 1-entry table: state never changes, no bits
-		for (u32 s = 0; s <= maxsym; s++) {
-			ct.dnb[s] = 0;
-			ct.dfs[s] = 0;
+		if (lane == 0) {
+			*p = (u8)most_sym;
+			ct.st[0] = 1;                 // a 1-entry table: state never changes, no bits
+			ct.dnb[most_sym] = 0u - 1u;   // (0 << 16) - (1 << 0): nbBits = (1 + dnb) >> 16 = 0
+			ct.dfs[most_sym] = -1;        // st[(1 >> 0) - 1] = st[0] = 1
 		}
-		ct.dnb[most_sym] = 0u - 1u;  // (0 << 16) - (1 << 0): nbBits = (1 + dnb) >> 16 = 0
-		ct.dfs[most_sym] = -1;       // st[(1 >> 0) - 1] = st[0] = 1
+		p++;
+		ct.log = 0;
+		__syncwarp();
 		return 1;
 	}
+	u32 deflog = predef.log;
 	u32 dyn_min = ((1u << deflog) * 8) >> 3;
 	if (maxsym <= defmax && (nseq < dyn_min || most < (nseq >> (deflog - 1)))) {  // Predefined_Mode
-		ct.log = deflog;
-		ze_fse_build_ctable(ct, defnorm, defmax, e.tsym, e.cumul);
+		ct = predef;
 		return 0;
 	}
 	u32 log = ze_fse_table_log(maxlog, nseq, maxsym);
-	ze_fse_normalize(e.norm, cnt, nseq, maxsym, log);
-	u32 nc = ze_fse_write_ncount(p, (u32)(end - p), e.norm, maxsym, log);
+	ze_fse_normalize_warp(e.norm, cnt, nseq, maxsym, log);
+	if (lane == 0) W->misc[3] = ze_fse_write_ncount(p, (u32)(end - p), e.norm, maxsym, log);
+	__syncwarp();
+	u32 nc = W->misc[3];
+	__syncwarp();
 	if (!nc) return 0xff;
 	p += nc;
 	ct.log = log;
-	ze_fse_build_ctable(ct, e.norm, maxsym, e.tsym, e.cumul);
+	ze_fse_build_ctable_warp(ct, e.norm, maxsym, e.tsym, e.cumul);
 	return 2;
 }
 
@@ -604,12 +714,35 @@ ZG_DEV u32 ze_seq_table(ZeEnt& e, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u
 // histogramming them -- is then done lane-parallel from the selection mask.
 ZG_DEV u32 ze_hash4(u32 v, u32 hlog) { return (v * 2654435761u) >> (32 - hlog); }
 
+// 16 bytes at an arbitrary address as four words.  Only aligned words are touched, and words that
+// start at or beyond `lim` read as zero (nothing past the block is dereferenced).
+ZG_DEV void ze_ld128(const u8* p, const u8* lim, u32 out[4]) {
+	uintptr_t a = (uintptr_t)p;
+	const u32* w = (const u32*)(a & ~(uintptr_t)3);
+	u32 sh = (u32)(a & 3) * 8;
+	u32 x[5];
+	ZG_UNROLL
+	for (int k = 0; k < 5; k++) x[k] = (const u8*)(w + k) < lim ? w[k] : 0u;
+	ZG_UNROLL
+	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
+}
+// number of leading equal bytes (0..16) of two 16-byte groups
+ZG_DEV u32 ze_eq16(const u32 a[4], const u32 b[4]) {
+	u32 x0 = a[0] ^ b[0], x1 = a[1] ^ b[1], x2 = a[2] ^ b[2], x3 = a[3] ^ b[3];
+	if (x0) return ((u32)__ffs((int)x0) - 1u) >> 3;
+	if (x1) return 4u + (((u32)__ffs((int)x1) - 1u) >> 3);
+	if (x2) return 8u + (((u32)__ffs((int)x2) - 1u) >> 3);
+	if (x3) return 12u + (((u32)__ffs((int)x3) - 1u) >> 3);
+	return 16u;
+}
+
 ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 lazy, u32* lit_count) {
 	u32 lane = zg_lane();
 	u32 ltmask = zg_lanemask_lt();
 	u32 hlog = 8;
 	while (hlog < ZE_HLOG_MAX && (1u << hlog) < n) hlog++;
 	u16* htab = W->u.htab;
+	const u8* lim = src + n;
 	{
 		u32* h32 = (u32*)htab;
 		for (u32 i = lane; i < (1u << hlog) / 2; i += 32) h32[i] = 0;
@@ -617,13 +750,15 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 laz
 	}
 	__syncwarp();
 	u32 mend = 0;      // end of the last match = start of the pending literals
-	u32 last_off = 0;  // its offset
 	u32 lpos = 0, nseq = 0, ip = 0;
 	while (ip < n && nseq < ZE_MAXSEQ - 32) {
 		u32 pos = ip + lane;
 		bool inb = pos < n;
 		bool valid = pos + 4 <= n;
-		u32 v = valid ? zg_ld32(src + pos) : (inb ? (u32)src[pos] : 0u);
+		zg_prefetch_l2(src + zg_min<u32>(ip + 2048u, n - 1u));
+		u32 own[4];
+		ze_ld128(src + pos, lim, own);
+		u32 v = own[0];
 		u32 h = valid ? ze_hash4(v, hlog) : (0x80000000u | lane);
 		u32 te = valid ? htab[h] : 0;
 		u32 peers = __match_any_sync(ZG_FULL, h);
@@ -641,45 +776,48 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 laz
 				cand = c;
 			}
 		}
+		// verify + extend, 16 bytes per memory round trip (both sides loaded before any compare)
 		u32 mlen = 0;
-		if (cand >= 0 && zg_ld32(src + cand) == v) {
-			u32 maxl = zg_min<u32>(n - pos, ZE_LANE_CAP);
-			mlen = 4;
-			while (mlen + 4 <= maxl) {
-				u32 x = zg_ld32(src + pos + mlen) ^ zg_ld32(src + cand + mlen);
-				if (x) {
-					mlen += ((u32)__ffs((int)x) - 1) >> 3;
-					break;
+		if (cand >= 0) {
+			u32 c[4];
+			ze_ld128(src + cand, lim, c);
+			if (c[0] == v) {
+				u32 maxl = zg_min<u32>(n - pos, ZE_LANE_CAP);
+				mlen = ze_eq16(own, c);
+				while (mlen < maxl && (mlen & 15u) == 0) {
+					u32 a[4];
+					ze_ld128(src + pos + mlen, lim, a);
+					ze_ld128(src + (u32)cand + mlen, lim, c);
+					u32 e = ze_eq16(a, c);
+					mlen += e;
+					if (e < 16) break;
 				}
-				mlen += 4;
+				mlen = zg_min<u32>(mlen, maxl);
 			}
-			if (mlen + 4 > maxl)
-				while (mlen < maxl && src[pos + mlen] == src[cand + mlen]) mlen++;
 		}
 		u32 moff = mlen ? pos - (u32)cand : 0;
 		__syncwarp();
-		// ---- selection (warp-uniform, as little as possible) ----
+		// ---- selection ----
+		// Greedy with one-step lazy evaluation, resolved without a per-candidate loop: a match is
+		// "good" unless the next position holds one that is more than a byte longer (the skipped
+		// lane's successor is then itself a candidate, so the first good lane at or after a position
+		// is exactly what the serial rule picks); every lane computes where the parse continues if
+		// it is taken (first good lane at or after its match end), and the warp only chases that
+		// chain from the first good lane.  A selected match is maximal for its offset, so the next
+		// one can never be "zero literals + same offset" (ze_assign_repcodes double-checks).
 		u32 has = __ballot_sync(ZG_FULL, mlen >= ZE_MINMATCH);
+		u32 mlen_up = __shfl_down_sync(ZG_FULL, mlen, 1);
+		bool skip = lazy && lane < 31 && mlen >= ZE_MINMATCH && mlen_up > mlen + 1;
+		u32 good = has & ~__ballot_sync(ZG_FULL, skip);
+		u32 t = lane + mlen;
+		u32 nxt = t < 32 ? (u32)__ffs((int)(good & ~((1u << t) - 1u))) - 1u : 0xffffffffu;
 		u32 sel = 0;
 		u32 cur = mend;
-		while (has) {
-			u32 i = (u32)__ffs((int)has) - 1;
+		for (u32 s = (u32)__ffs((int)good) - 1u; s < 32u; s = __shfl_sync(ZG_FULL, nxt, (int)s)) sel |= 1u << s;
+		if (sel) {
+			u32 i = 31u - (u32)__clz((int)sel);  // only the last selected match can leave the window
 			u32 L = __shfl_sync(ZG_FULL, mlen, (int)i), O = __shfl_sync(ZG_FULL, moff, (int)i);
-			if (lazy && i < 31 && ((has >> (i + 1)) & 1)) {
-				u32 L1 = __shfl_sync(ZG_FULL, mlen, (int)i + 1);
-				if (L1 > L + 1) {
-					has &= ~(1u << i);
-					continue;
-				}
-			}
 			u32 p = ip + i;
-			if (p == cur && O == last_off && (nseq | sel)) {
-				// would continue the previous match with a zero literal length and the same offset: the
-				// repeat-offset model below relies on this never being emitted (maximal matches make it
-				// impossible in practice)
-				has &= ~(1u << i);
-				continue;
-			}
 			if (L >= ZE_LANE_CAP && p + L < n) {
 				// whole-warp extension, 128 bytes per step
 				for (;;) {
@@ -702,11 +840,7 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 laz
 				}
 				if (lane == i) mlen = L;
 			}
-			sel |= 1u << i;
-			last_off = O;
 			cur = p + L;
-			u32 rel = cur - ip;
-			has = rel >= 32 ? 0 : (has & ~((1u << rel) - 1u));
 		}
 		// ---- emission (lane-parallel) ----
 		u32 below = sel & ltmask;
@@ -834,7 +968,7 @@ ZG_DEV bool ze_assign_repcodes(ZeWarp* W, ZeScratch* S, u32 nseq, bool first_blo
 // ---------------------------------------------------------------------------------------------
 // K3: entropy-code the block into dst[0..cap).  Returns the body size, or 0 if it would not be
 // smaller than the raw block.  All lanes call.
-ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZeScratch* S, u32 nseq, u32 nlit, u8* dst, u32 cap) {
+ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 nlit, u8* dst, u32 cap) {
 	ZeEnt& e = W->u.e;
 	u32 lane = zg_lane();
 	if (cap < 16) return 0;
@@ -984,42 +1118,57 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZeScratch* S, u32 nseq, u32 nlit, u8* dst
 	mx_ml = zg_warp_max(mx_ml);
 	mx_of = zg_warp_max(mx_of);
 	__syncwarp();
-	if (lane == 0) {
-		bool ok = true;
+	ZeCT ct3[3];  // LL, ML, OF
+	u32 bs_off;
+	{
 		u8* q = p + 1;  // after the modes byte
-		ZeCT ct_ll, ct_ml, ct_of;
-		u32 m_ll = ze_seq_table(e, 0, e.hist3[0], nseq, mx_ll, ZS_LL_MAXLOG, 6, ZS_LL_DEFAULT_NORM, 35, q, end, ct_ll);
-		u32 m_of = m_ll == 0xff ? 0xff : ze_seq_table(e, 2, e.hist3[2], nseq, mx_of, ZS_OF_MAXLOG, 5, ZS_OF_DEFAULT_NORM, 28, q, end, ct_of);
-		u32 m_ml = m_of == 0xff ? 0xff : ze_seq_table(e, 1, e.hist3[1], nseq, mx_ml, ZS_ML_MAXLOG, 6, ZS_ML_DEFAULT_NORM, 52, q, end, ct_ml);
-		if (m_ll == 0xff || m_of == 0xff || m_ml == 0xff) ok = false;
-		if (ok) *p = (u8)((m_ll << 6) | (m_of << 4) | (m_ml << 2));
-		W->misc[1] = ok ? 1 : 0;
-		W->misc[2] = (u32)(q - dst);
-		W->misc[4] = ct_ll.log;
-		W->misc[5] = ct_ml.log;
-		W->misc[6] = ct_of.log;
+		ZeCT pd_ll{P->st_ll, P->dnb_ll, P->dfs_ll, 6}, pd_ml{P->st_ml, P->dnb_ml, P->dfs_ml, 6}, pd_of{P->st_of, P->dnb_of, P->dfs_of, 5};
+		u32 m_ll = ze_seq_table(W, pd_ll, 0, e.hist3[0], nseq, mx_ll, ZS_LL_MAXLOG, 35, q, end, ct3[0]);
+		if (m_ll == 0xff) return 0;
+		u32 m_of = ze_seq_table(W, pd_of, 2, e.hist3[2], nseq, mx_of, ZS_OF_MAXLOG, 28, q, end, ct3[2]);
+		if (m_of == 0xff) return 0;
+		u32 m_ml = ze_seq_table(W, pd_ml, 1, e.hist3[1], nseq, mx_ml, ZS_ML_MAXLOG, 52, q, end, ct3[1]);
+		if (m_ml == 0xff) return 0;
+		if (lane == 0) *p = (u8)((m_ll << 6) | (m_of << 4) | (m_ml << 2));
+		bs_off = (u32)(q - dst);
 	}
-	__syncwarp();
-	if (!W->misc[1]) return 0;
-	u32 bs_off = W->misc[2];
-	u32 logs[3] = {W->misc[4], W->misc[5], W->misc[6]};
+	u32 logs[3] = {ct3[0].log, ct3[1].log, ct3[2].log};
 	__syncwarp();
 	// Phase 1: the three FSE state chains are independent of each other -> lanes 0,1,2 walk one
 	// each (last sequence first, libzstd's ZSTD_encodeSequences order), leaving per sequence the
-	// bits that chain emits (value | nbBits << 12).
+	// bits that chain emits (value | nbBits << 12).  Four steps per trip: the symbol codes and
+	// their table rows are fetched up front, only the state look-ups are serial.
 	if (lane < 3) {
 		u32 t = lane, sh = 8 * lane;  // codes = ll | ml << 8 | of << 16; table index 0 LL, 1 ML, 2 OF
-		ZeCT ct{e.st[t], e.dnb[t], e.dfs[t], logs[t]};
+		ZeCT ct = lane == 0 ? ct3[0] : lane == 1 ? ct3[1] : ct3[2];
 		u16* out = S->stb[t];
 		u32 state = ze_fse_init_state(ct, (S->codes[nseq - 1] >> sh) & 0xff);
 		out[nseq - 1] = 0;
-		for (u32 i = nseq - 1; i-- > 0;) {
+		u32 i = nseq - 1;
+		while (i >= 4) {
+			u32 d[4];
+			i32 f[4];
+			ZG_UNROLL
+			for (int k = 0; k < 4; k++) {
+				u32 code = (S->codes[i - 1 - k] >> sh) & 0xff;
+				d[k] = ct.dnb[code];
+				f[k] = ct.dfs[code];
+			}
+			ZG_UNROLL
+			for (int k = 0; k < 4; k++) {
+				u32 nb = (state + d[k]) >> 16;
+				out[i - 1 - k] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+				state = ct.st[(state >> nb) + f[k]];
+			}
+			i -= 4;
+		}
+		while (i-- > 0) {
 			u32 code = (S->codes[i] >> sh) & 0xff;
 			u32 nb = (state + ct.dnb[code]) >> 16;
 			out[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
 			state = ct.st[(state >> nb) + ct.dfs[code]];
 		}
-		W->misc[8 + t] = state & ((1u << logs[t]) - 1u);
+		W->misc[8 + t] = state & ((1u << ct.log) - 1u);
 	}
 	__syncwarp();
 	// Phase 2: every lane assembles one sequence's bit field (<= 89 bits: OF,ML,LL state bits then
@@ -1078,7 +1227,7 @@ struct ZeParams {
 	u32 window;    // reserved
 };
 
-__global__ void __launch_bounds__(ZE_WARPS * 32)
+__global__ void __launch_bounds__(ZE_WARPS * 32, ZE_MIN_CTAS)
 k_zstd_encode_blocks(const u8* __restrict__ blob, const u64* __restrict__ file_off, const u64* __restrict__ comp_off,
                      const u64* __restrict__ file_len,
                      const u32* __restrict__ ulist, const u64* __restrict__ blk_base, u32 nuniq, u64 nblocks, u8* comp,
@@ -1086,7 +1235,15 @@ k_zstd_encode_blocks(const u8* __restrict__ blob, const u64* __restrict__ file_o
 	ZG_DYN_SMEM(ZeWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZeWarp* W = &sm[warp];
+	ZePredef* P = (ZePredef*)(sm + ZE_WARPS);
 	ZeScratch* S = scratch + (size_t)(blockIdx.x * ZE_WARPS + warp);
+	if (threadIdx.x == 0) {  // the predefined compression tables, once per (persistent) CTA
+		ZeEnt& e = W->u.e;
+		ze_fse_build_ctable(ZeCT{P->st_ll, P->dnb_ll, P->dfs_ll, 6}, ZS_LL_DEFAULT_NORM, 35, e.tsym, e.cumul);
+		ze_fse_build_ctable(ZeCT{P->st_ml, P->dnb_ml, P->dfs_ml, 6}, ZS_ML_DEFAULT_NORM, 52, e.tsym, e.cumul);
+		ze_fse_build_ctable(ZeCT{P->st_of, P->dnb_of, P->dfs_of, 5}, ZS_OF_DEFAULT_NORM, 28, e.tsym, e.cumul);
+	}
+	__syncthreads();
 	for (;;) {
 		u32 b = 0;
 		if (lane == 0) b = atomicAdd(queue, 1u);
@@ -1113,7 +1270,7 @@ k_zstd_encode_blocks(const u8* __restrict__ blob, const u64* __restrict__ file_o
 			__syncwarp();
 			// later blocks of a frame are encoded independently of their predecessors: unknown history
 			if (ze_assign_repcodes(W, S, nseq, j == 0))
-				csize = ze_entropy_block(W, S, nseq, nlit, dst, n - 1);
+				csize = ze_entropy_block(W, P, S, nseq, nlit, dst, n - 1);
 			__syncwarp();
 		}
 		__syncwarp();
@@ -1125,13 +1282,13 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
                           const u32* ulist,
                           const u64* blk_base, u32 nuniq, u64 nblocks, u8* comp, u32* blk_csize, int level) {
 	if (nblocks == 0) return 0;
-	u32 grid = (u32)zg_min<u64>((nblocks + ZE_WARPS - 1) / ZE_WARPS, (u64)zg_sm_count() * 3);
+	u32 grid = (u32)zg_min<u64>((nblocks + ZE_WARPS - 1) / ZE_WARPS, (u64)zg_sm_count() * ZE_MIN_CTAS);
 	if (w.scratch.reserve((size_t)grid * ZE_WARPS * sizeof(ZeScratch)) || w.queue.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.queue.p, 0, 16, s);
 	ZeParams prm;
 	prm.lazy = level >= 3 ? 1 : 0;
 	prm.window = 0;
-	size_t smem = sizeof(ZeWarp) * ZE_WARPS;
+	size_t smem = sizeof(ZeWarp) * ZE_WARPS + sizeof(ZePredef);
 	static bool attr_set = false;
 	if (!attr_set) {
 		if (cudaFuncSetAttribute(k_zstd_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
