@@ -154,7 +154,7 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 		                         nblocks));
 		// (3) compress every new content (content_frame.rs:41 -> lowlevel_frames.rs:30)
 		ZG_TRY(zg_zstd_encode_run(s, c->ze, blob, off, c->comp_off.as<u64>(), len, c->ulist.as<u32>(), c->blk_base.as<u64>(), (u32)nuniq,
-		                          nblocks, c->comp.as<u8>(), c->blk_csize.as<u32>(), c->level));
+		                          nblocks, comp_bytes, c->comp.as<u8>(), c->blk_csize.as<u32>(), c->level));
 		if (c->checksum) ZG_TRY(zg_pk_xxh64_list(s, blob, off, len, c->ulist.as<u32>(), nuniq, c->xxh.as<u64>()));
 		// (4) frame lengths -> archive offsets (content_frame.rs:22,45)
 		ZG_TRY(zg_pk_block_out_sizes(s, c->blk_csize.as<u32>(), nblocks, c->blk_out.as<u64>()));
@@ -203,8 +203,7 @@ void zg_cctx_free(zg_cctx* c) {
 	c->archive.release();
 	c->oneshot.release();
 	zg_b3work_free(c->b3);
-	c->ze.scratch.release();
-	c->ze.queue.release();
+	c->ze.release();
 	for (ZgBuf* b : {&c->tiles, &c->rep, &c->isfirst64, &c->nblk, &c->clen, &c->uidx, &c->blkfirst, &c->comp_off, &c->ulist, &c->blk_base,
 	                 &c->blk_csize, &c->blk_out, &c->blk_pos, &c->frame_len_u, &c->frame_off_u, &c->xxh, &c->comp, &c->totals, &c->first_tmp,
 	                 &c->d_blob, &c->d_meta, &c->d_out_meta, &c->d_frames})

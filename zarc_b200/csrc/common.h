@@ -95,12 +95,17 @@ size_t zg_first_error_run(cudaStream_t s, const u32* status, u64 n, u64* first);
 
 // ---- zstd_encode.cu ----
 struct ZgZeWork {
-	ZgBuf scratch;  // per-warp sequence/literal staging
-	ZgBuf queue;
+	ZgBuf queue;    // per chunk: per kernel block counters + the table-arena counter
+	ZgBuf meta;     // per block: what one kernel hands to the next
+	ZgBuf seqbuf, litbuf, codebuf, stbbuf;  // per chunk staging between (and inside) the kernels
+	ZgBuf bounds;   // first block of every chunk
+	void release() {
+		for (ZgBuf* b : {&queue, &meta, &seqbuf, &litbuf, &codebuf, &stbbuf, &bounds}) b->release();
+	}
 };
 size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
-                          const u32* ulist,
-                          const u64* blk_base, u32 nuniq, u64 nblocks, u8* comp, u32* blk_csize, int level);
+                          const u32* ulist, const u64* blk_base, u32 nuniq, u64 nblocks, u64 comp_bytes, u8* comp, u32* blk_csize,
+                          int level);
 
 // ---- per-kernel device timing (abi.cu): CUDA events on the launching stream, off by default ----
 enum { ZG_K_BLAKE3 = 0, ZG_K_ENCODE = 1, ZG_K_DECODE = 2, ZG_K_ASSEMBLE = 3, ZG_K_XXH64 = 4, ZG_K_DEDUP = 5, ZG_K_COUNT = 6 };

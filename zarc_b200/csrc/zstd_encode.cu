@@ -2,7 +2,12 @@
 // crates/zarc/src/encode/lowlevel_frames.rs:30 (libzstd 1.5.5 in the reference).  Compressed bytes
 // are not required to equal libzstd's; every block must be valid RFC 8878 that libzstd restores.
 //
-// One warp per <=128 KiB block, pulled from an atomic queue.
+// Three kernels per chunk of blocks (K2 match -> K3a literals -> K3b sequences), one warp per
+// <=128 KiB block pulled from an atomic queue in each.  Splitting by phase keeps every kernel's hot
+// code inside the instruction cache (one fused kernel spent 20-35 % of its issue slots waiting for
+// instruction fetch) and lets each phase size its own shared memory.  Sequences and literals pass
+// between the kernels through a staging area laid out like the chunk's input (a block's sequences
+// at 2x, its literals at 1x its offset inside the chunk).
 //   K2 match finding: the warp hashes 32 consecutive positions at a time (4-byte hash) against a
 //      shared-memory table of 16-bit positions (64 KiB window inside the block), also matching
 //      lanes against each other (__match_any_sync) for distances < 32; every lane verifies and
@@ -18,11 +23,18 @@
 
 #define ZE_WARPS 4
 #ifndef ZE_HLOG_MAX
-#define ZE_HLOG_MAX 13
+#define ZE_HLOG_MAX 12
 #endif
 #ifndef ZE_MIN_CTAS
-#define ZE_MIN_CTAS 3
+#define ZE_MIN_CTAS 6   // K2: CTAs per SM
 #endif
+#ifndef ZE_ENT_CTAS
+#define ZE_ENT_CTAS 6   // K3a/K3b: CTAs per SM
+#endif
+#ifndef ZE_CHUNK_BYTES
+#define ZE_CHUNK_BYTES (1ull << 30)  // input bytes per chunk (staging between the kernels = 6x this)
+#endif
+#define ZE_NQ 4  // queue counters per chunk (one per kernel)
 #define ZE_MAXSEQ 32768u
 #define ZE_MINMATCH 4u
 #define ZE_LANE_CAP 64u   // per-lane match extension cap; longer matches are extended by the whole warp
@@ -40,11 +52,18 @@ ZG_DEV u32 ze_ml_code(u32 mlbase) { return mlbase < 128 ? ZS_ML_CODE[mlbase] : z
 #define ZE_SEQ_LL(q) ((u32)((q) >> 17) & 0x1ffffu)
 #define ZE_SEQ_ML(q) ((u32)((q) >> 34))
 #define ZE_SEQ_PACK(of, ll, ml) ((u64)(of) | ((u64)(ll) << 17) | ((u64)(ml) << 34))
-struct ZeScratch {
-	u64 seq[ZE_MAXSEQ];
-	u32 codes[ZE_MAXSEQ]; // ll | ml << 8 | of << 16
-	u16 stb[3][ZE_MAXSEQ]; // per sequence, per table (LL, ML, OF): FSE state bits value | nbBits << 12
-	u8 lit[ZS_BLOCK_MAX + 64];
+struct ZeBlkMeta {       // per block, handed from kernel to kernel
+	u32 nseq;            // ZE_RAW: store the block raw
+	u32 nlit;
+	u32 litsec;          // size of the literals section K3a wrote (0: give up, store raw)
+	u32 logs;            // (K3b, in registers) table logs LL | ML << 8 | OF << 16
+	u32 fin[3];          // (K3b, in registers) final states LL, ML, OF (low `log` bits)
+	u32 pad;
+};
+// symbolTT row as the chains read it
+struct ZeSymTT {
+	u32 dnb;
+	i32 dfs;
 };
 
 struct ZeEnt {
@@ -60,8 +79,7 @@ struct ZeEnt {
 		};
 		struct {
 			u16 st[3][512];   // FSE state tables: LL, ML, OF (OF also serves the Huffman-weight table)
-			u32 dnb[3][64];   // symbolTT.deltaNbBits
-			i32 dfs[3][64];   // symbolTT.deltaFindState
+			ZeSymTT tt[3][64]; // symbolTT rows: deltaNbBits, deltaFindState
 			u32 hist3[3][64];
 		};
 	};
@@ -71,13 +89,14 @@ struct ZeEnt {
 	u8 wdesc[192];        // Huffman tree description staging
 	u32 window[96];       // bit-packing window (384 B)
 };
-struct ZeWarp {
-	union {
-		u16 htab[1 << ZE_HLOG_MAX];
-		ZeEnt e;
-	} u;
+struct ZeWarp {          // K3a / K3b
+	ZeEnt e;
 	u32 hist[256];
 	u32 misc[16];
+};
+struct ZeMatchWarp {     // K2
+	u16 htab[1 << ZE_HLOG_MAX];
+	u32 ring[48];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -126,20 +145,20 @@ ZG_DEV u8* ze_bw_close(ZeBitW& w) {
 // FSE compression tables (libzstd's formulation: state table + per-symbol deltaNbBits/deltaFindState)
 struct ZeCT {
 	u16* st;
-	u32* dnb;
-	i32* dfs;
+	ZeSymTT* tt;
 	u32 log;
 };
 ZG_DEV u32 ze_fse_init_state(const ZeCT& ct, u32 sym) {  // FSE_initCState2: smallest state of sym
-	u32 d = ct.dnb[sym];
-	u32 nb = (d + (1u << 15)) >> 16;
-	u32 v = (nb << 16) - d;
-	return ct.st[(v >> nb) + ct.dfs[sym]];
+	ZeSymTT r = ct.tt[sym];
+	u32 nb = (r.dnb + (1u << 15)) >> 16;
+	u32 v = (nb << 16) - r.dnb;
+	return ct.st[(v >> nb) + r.dfs];
 }
 ZG_DEV void ze_fse_encode(ZeBitW& w, const ZeCT& ct, u32& state, u32 sym) {
-	u32 nb = (state + ct.dnb[sym]) >> 16;
+	ZeSymTT r = ct.tt[sym];
+	u32 nb = (state + r.dnb) >> 16;
 	ze_bw_add(w, state, nb);
-	state = ct.st[(state >> nb) + ct.dfs[sym]];
+	state = ct.st[(state >> nb) + r.dfs];
 }
 ZG_DEV void ze_fse_flush_state(ZeBitW& w, const ZeCT& ct, u32 state) { ze_bw_add(w, state, ct.log); }
 
@@ -173,17 +192,14 @@ ZG_DEV_NOINLINE void ze_fse_build_ctable(const ZeCT& ct, const i16* norm, u32 ma
 	for (u32 s = 0; s <= maxsym; s++) {
 		i32 n = norm[s];
 		if (n == 0) {
-			ct.dnb[s] = ((log + 1) << 16) - size;
-			ct.dfs[s] = 0;
+			ct.tt[s] = ZeSymTT{((log + 1) << 16) - size, 0};
 		} else if (n == 1 || n == -1) {
-			ct.dnb[s] = (log << 16) - size;
-			ct.dfs[s] = (i32)total - 1;
+			ct.tt[s] = ZeSymTT{(log << 16) - size, (i32)total - 1};
 			total += 1;
 		} else {
 			u32 maxbits = log - zs_highbit((u32)n - 1);
 			u32 minstate = (u32)n << maxbits;
-			ct.dnb[s] = (maxbits << 16) - minstate;
-			ct.dfs[s] = (i32)total - n;
+			ct.tt[s] = ZeSymTT{(maxbits << 16) - minstate, (i32)total - n};
 			total += (u32)n;
 		}
 	}
@@ -251,15 +267,12 @@ ZG_DEV_NOINLINE void ze_fse_build_ctable_warp(const ZeCT& ct, const i16* norm, u
 		u32 s = k ? s1 : s0, n = k ? n1 : n0, ex = k ? ex1 : ex0;
 		if (s > maxsym) continue;
 		if (n == 0) {
-			ct.dnb[s] = ((log + 1) << 16) - size;
-			ct.dfs[s] = 0;
+			ct.tt[s] = ZeSymTT{((log + 1) << 16) - size, 0};
 		} else if (n == 1) {
-			ct.dnb[s] = (log << 16) - size;
-			ct.dfs[s] = (i32)ex - 1;
+			ct.tt[s] = ZeSymTT{(log << 16) - size, (i32)ex - 1};
 		} else {
 			u32 maxbits = log - zs_highbit(n - 1);
-			ct.dnb[s] = (maxbits << 16) - (n << maxbits);
-			ct.dfs[s] = (i32)ex - (i32)n;
+			ct.tt[s] = ZeSymTT{(maxbits << 16) - (n << maxbits), (i32)ex - (i32)n};
 		}
 	}
 	__syncwarp();
@@ -369,7 +382,7 @@ ZG_DEV_NOINLINE u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 m
 // Huffman: code lengths (<= 11 bits) from the literal histogram.  Returns maxBits (0 = failure),
 // fills e.hweight[0..maxsym], e.hcode[], *maxsym_out.  All lanes call.
 ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
-	ZeEnt& e = W->u.e;
+	ZeEnt& e = W->e;
 	u32 lane = zg_lane();
 	// present symbols, ascending symbol order -> node_cnt/node_par as (cnt, sym) staging
 	u32 n = 0;
@@ -452,7 +465,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 
 // Huffman tree description into e.wdesc (single lane).  Returns its size, 0 if not representable.
 ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
-	ZeEnt& e = W->u.e;
+	ZeEnt& e = W->e;
 	u32 nw = maxsym;  // weights 0..maxsym-1 are explicit, the last is implied
 	u32 direct = nw <= 128 ? 1 + ((nw + 1) >> 1) : 0;
 	u32 fse_size = 0;
@@ -471,7 +484,7 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 			ze_fse_normalize(e.norm, cnt, nw, maxw, log);
 			u32 nc = ze_fse_write_ncount(e.wdesc + 1, 127, e.norm, maxw, log);
 			if (nc) {
-				ZeCT ct{e.st[2], e.dnb[2], e.dfs[2], log};
+				ZeCT ct{e.st[2], e.tt[2], log};
 				ze_fse_build_ctable(ct, e.norm, maxw, e.tsym, e.cumul);
 				ZeBitW bw;
 				ze_bw_init(bw, e.wdesc + 1 + nc, e.wdesc + 128);
@@ -520,7 +533,7 @@ ZG_DEV_NOINLINE u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
 // One Huffman stream for lit[0..m) into dst (exactly `nbytes` bytes, as computed from count_bits).
 // The last literal is written first (lowest bits); parallel bit packing through a shared window.
 ZG_DEV_NOINLINE void ze_huf_encode_stream(ZeWarp* W, const u8* lit, u32 m, u8* dst, u32 total_bits) {
-	ZeEnt& e = W->u.e;
+	ZeEnt& e = W->e;
 	u32 lane = zg_lane();
 	u32* win = e.window;  // 96 words
 	u32 bitpos = 0;       // bits already flushed to dst (multiple of 8) + bits pending in window
@@ -658,26 +671,23 @@ ZG_DEV u32 ze_pack_finish(ZePack& P) {
 // The predefined tables are built once per CTA (ZePredef); only FSE_Compressed tables are built here.
 struct ZePredef {
 	u16 st_ll[64], st_ml[64], st_of[32];
-	u32 dnb_ll[36], dnb_ml[53], dnb_of[29];
-	i32 dfs_ll[36], dfs_ml[53], dfs_of[29];
+	ZeSymTT tt_ll[36], tt_ml[53], tt_of[29];
 };
 ZG_DEV_NOINLINE u32 ze_seq_table(ZeWarp* W, const ZeCT& predef, u32 t, const u32* cnt, u32 nseq, u32 maxsym, u32 maxlog, u32 defmax, u8*& p,
-                        u8* end, ZeCT& ct) {
-	ZeEnt& e = W->u.e;
+                                 u8* end, ZeCT& ct) {
+	ZeEnt& e = W->e;
 	u32 lane = zg_lane();
 	u32 c0 = lane <= maxsym ? cnt[lane] : 0u, c1 = lane + 32 <= maxsym ? cnt[lane + 32] : 0u;
 	u32 key = zg_warp_max(zg_max<u32>((c0 << 6) | (63u - lane), (c1 << 6) | (31u - lane)));
 	u32 most = key >> 6, most_sym = 63u - (key & 63u);
 	ct.st = e.st[t];
-	ct.dnb = e.dnb[t];
-	ct.dfs = e.dfs[t];
+	ct.tt = e.tt[t];
 	if (most == nseq && nseq > 2) {  // RLE_Mode
 		if (p >= end) return 0xff;
 		if (lane == 0) {
 			*p = (u8)most_sym;
 			ct.st[0] = 1;                 // a 1-entry table: state never changes, no bits
-			ct.dnb[most_sym] = 0u - 1u;   // (0 << 16) - (1 << 0): nbBits = (1 + dnb) >> 16 = 0
-			ct.dfs[most_sym] = -1;        // st[(1 >> 0) - 1] = st[0] = 1
+			ct.tt[most_sym] = ZeSymTT{0u - 1u, -1};  // dnb = (0 << 16) - (1 << 0): no bits; st[(1 >> 0) - 1] = st[0] = 1
 		}
 		p++;
 		ct.log = 0;
@@ -687,7 +697,12 @@ ZG_DEV_NOINLINE u32 ze_seq_table(ZeWarp* W, const ZeCT& predef, u32 t, const u32
 	u32 deflog = predef.log;
 	u32 dyn_min = ((1u << deflog) * 8) >> 3;
 	if (maxsym <= defmax && (nseq < dyn_min || most < (nseq >> (deflog - 1)))) {  // Predefined_Mode
-		ct = predef;
+		// copy the CTA's predefined table into this warp's slot: the chains address all three
+		// tables of a block uniformly
+		for (u32 i = lane; i < (1u << deflog); i += 32) ct.st[i] = predef.st[i];
+		for (u32 i = lane; i <= defmax; i += 32) ct.tt[i] = predef.tt[i];
+		ct.log = deflog;
+		__syncwarp();
 		return 0;
 	}
 	u32 log = ze_fse_table_log(maxlog, nseq, maxsym);
@@ -736,17 +751,16 @@ ZG_DEV u32 ze_eq16(const u32 a[4], const u32 b[4]) {
 	return 16u;
 }
 
-ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 lazy, u32* lit_count) {
+ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 n, u32 lazy, u32* lit_count) {
 	u32 lane = zg_lane();
 	u32 ltmask = zg_lanemask_lt();
 	u32 hlog = 8;
 	while (hlog < ZE_HLOG_MAX && (1u << hlog) < n) hlog++;
-	u16* htab = W->u.htab;
+	u16* htab = W->htab;
 	const u8* lim = src + n;
 	{
 		u32* h32 = (u32*)htab;
 		for (u32 i = lane; i < (1u << hlog) / 2; i += 32) h32[i] = 0;
-		for (u32 i = lane; i < 256; i += 32) W->hist[i] = 0;
 	}
 	__syncwarp();
 	u32 mend = 0;      // end of the last match = start of the pending literals
@@ -848,14 +862,10 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 laz
 		u32 pend = __shfl_sync(ZG_FULL, my_end, below ? (int)(31u - (u32)__clz((int)below)) : 0);
 		u32 prev_end = below ? pend : mend;  // end of the nearest match that starts before this position
 		bool selme = (sel >> lane) & 1u;
-		if (selme) S->seq[nseq + (u32)__popc(below)] = ZE_SEQ_PACK(moff, pos - prev_end, mlen);
+		if (selme) seq[nseq + (u32)__popc(below)] = ZE_SEQ_PACK(moff, pos - prev_end, mlen);
 		bool is_lit = inb && !selme && pos >= prev_end;
 		u32 lm = __ballot_sync(ZG_FULL, is_lit);
-		if (is_lit) {
-			u32 b = v & 0xffu;
-			S->lit[lpos + (u32)__popc(lm & ltmask)] = (u8)b;
-			atomicAdd(&W->hist[b], 1u);
-		}
+		if (is_lit) lit[lpos + (u32)__popc(lm & ltmask)] = (u8)v;
 		lpos += (u32)__popc(lm);
 		nseq += (u32)__popc(sel);
 		mend = cur;
@@ -865,11 +875,7 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 laz
 	{
 		u32 start = zg_max<u32>(ip, mend);
 		u32 rest = start < n ? n - start : 0;
-		for (u32 k = lane; k < rest; k += 32) {
-			u32 b = src[start + k];
-			S->lit[lpos + k] = (u8)b;
-			atomicAdd(&W->hist[b], 1u);
-		}
+		for (u32 k = lane; k < rest; k += 32) lit[lpos + k] = src[start + k];
 		lpos += rest;
 	}
 	__syncwarp();
@@ -887,9 +893,9 @@ ZG_DEV u32 ze_match_block(ZeWarp* W, ZeScratch* S, const u8* src, u32 n, u32 laz
 // never match.  Rewrites S->seq[i].of from offset to offBase.  Returns false if the impossible
 // transition is met (the caller then stores the block raw).
 #define ZE_REP_LOOKBACK 8u
-ZG_DEV bool ze_assign_repcodes(ZeWarp* W, ZeScratch* S, u32 nseq, bool first_block) {
+ZG_DEV bool ze_assign_repcodes(ZeMatchWarp* W, u64* seq, u32 nseq, bool first_block) {
 	u32 lane = zg_lane();
-	u32* ro = W->u.e.window;  // [ZE_REP_LOOKBACK + 32] offsets: the previous chunk's tail, then this chunk
+	u32* ro = W->ring;  // [ZE_REP_LOOKBACK + 32] offsets: the previous chunk's tail, then this chunk
 	if (lane < ZE_REP_LOOKBACK) ro[lane] = 0;
 	__syncwarp();
 	u32 a_carry = 0, b_carry = 0;
@@ -907,7 +913,7 @@ ZG_DEV bool ze_assign_repcodes(ZeWarp* W, ZeScratch* S, u32 nseq, bool first_blo
 	for (u32 s0 = 0; s0 < nseq; s0 += 32) {
 		u32 cnt = zg_min<u32>(32u, nseq - s0);
 		bool act = lane < cnt;
-		u64 q = act ? S->seq[s0 + lane] : 0;
+		u64 q = act ? seq[s0 + lane] : 0;
 		u32 O = ZE_SEQ_OF(q), ll = ZE_SEQ_LL(q);
 		u32 olast = __shfl_sync(ZG_FULL, O, (int)cnt - 1);
 		if (!act) O = olast;  // idle lanes repeat the last offset: no change points
@@ -953,7 +959,7 @@ ZG_DEV bool ze_assign_repcodes(ZeWarp* W, ZeScratch* S, u32 nseq, bool first_blo
 			else if (a > 1 && O == a - 1) ofb = 3;
 			else ofb = O + 3;
 		}
-		if (act) S->seq[s0 + lane] = ZE_SEQ_PACK(ofb, ll, ZE_SEQ_ML(q));
+		if (act) seq[s0 + lane] = ZE_SEQ_PACK(ofb, ll, ZE_SEQ_ML(q));
 		a_carry = __shfl_sync(ZG_FULL, O, 31);
 		b_carry = __shfl_sync(ZG_FULL, b_after, 31);
 		__syncwarp();
@@ -966,15 +972,29 @@ ZG_DEV bool ze_assign_repcodes(ZeWarp* W, ZeScratch* S, u32 nseq, bool first_blo
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: entropy-code the block into dst[0..cap).  Returns the body size, or 0 if it would not be
-// smaller than the raw block.  All lanes call.
-ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 nlit, u8* dst, u32 cap) {
-	ZeEnt& e = W->u.e;
+// K3a: the literals section of one block into dst[0..cap).  Returns its size, or 0 if the block
+// cannot end up smaller than raw.  All lanes call.
+ZG_DEV u32 ze_literals_section(ZeWarp* W, const u8* lit, u32 nlit, u8* dst, u32 cap) {
+	ZeEnt& e = W->e;
 	u32 lane = zg_lane();
 	if (cap < 16) return 0;
 	u8* end = dst + cap;
 	u8* p = dst;
-	// ---- literals section ----
+	for (u32 i = lane; i < 256; i += 32) W->hist[i] = 0;
+	__syncwarp();
+	for (u32 i0 = 0; i0 < nlit; i0 += 128) {  // 4 literals per lane per trip
+		u32 i = i0 + 4 * lane;
+		if (i + 4 <= nlit) {
+			u32 w = *(const u32*)(lit + i);  // the literal buffer of a block is 16-byte aligned
+			atomicAdd(&W->hist[w & 0xff], 1u);
+			atomicAdd(&W->hist[(w >> 8) & 0xff], 1u);
+			atomicAdd(&W->hist[(w >> 16) & 0xff], 1u);
+			atomicAdd(&W->hist[w >> 24], 1u);
+		} else {
+			for (; i < nlit; i++) atomicAdd(&W->hist[lit[i]], 1u);
+		}
+	}
+	__syncwarp();
 	u32 maxc = 0;
 	for (u32 k = 0; k < 8; k++) maxc = zg_max<u32>(maxc, W->hist[k * 32 + lane]);
 	maxc = zg_warp_max(maxc);
@@ -996,13 +1016,13 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 		}
 		if (tree) {
 			if (streams == 1) {
-				sbits[0] = ze_huf_count_bits(e, S->lit, nlit);
+				sbits[0] = ze_huf_count_bits(e, lit, nlit);
 				sbytes[0] = (sbits[0] + 8) >> 3;
 				comp = tree + sbytes[0];
 			} else {
 				for (u32 k = 0; k < 4; k++) {
 					u32 m = k < 3 ? seg : nlit - 3 * seg;
-					sbits[k] = ze_huf_count_bits(e, S->lit + k * seg, m);
+					sbits[k] = ze_huf_count_bits(e, lit + k * seg, m);
 					sbytes[k] = (sbits[k] + 8) >> 3;
 				}
 				comp = tree + 6 + sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
@@ -1036,7 +1056,7 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 		for (u32 i = lane; i < tree; i += 32) p[i] = e.wdesc[i];
 		p += tree;
 		if (streams == 1) {
-			ze_huf_encode_stream(W, S->lit, nlit, p, sbits[0]);
+			ze_huf_encode_stream(W, lit, nlit, p, sbits[0]);
 			p += sbytes[0];
 		} else {
 			if (lane == 0) {
@@ -1050,7 +1070,7 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 			p += 6;
 			for (u32 k = 0; k < 4; k++) {
 				u32 m = k < 3 ? seg : nlit - 3 * seg;
-				ze_huf_encode_stream(W, S->lit + k * seg, m, p, sbits[k]);
+				ze_huf_encode_stream(W, lit + k * seg, m, p, sbits[k]);
 				p += sbytes[k];
 			}
 		}
@@ -1073,19 +1093,29 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 		}
 		p += hdr;
 		if (mode == 1) {
-			if (lane == 0) p[0] = S->lit[0];
+			if (lane == 0) p[0] = lit[0];
 		} else {
-			for (u32 i = lane; i < nlit; i += 32) p[i] = S->lit[i];
+			for (u32 i = lane; i < nlit; i += 32) p[i] = lit[i];
 		}
 		p += payload;
 	}
 	__syncwarp();
-	// ---- sequences section ----
+	__syncwarp();
+	return (u32)(p - dst);
+}
+
+// K3b1: sequence codes + histograms, table modes, table descriptions into dst[0..cap) (dst = just
+// after the literals section), compression tables into the table arena.  Returns the bytes written
+// (header + descriptions), 0 when it does not fit.  All lanes call.
+ZG_DEV u32 ze_sequences_tables(ZeWarp* W, ZePredef* P, const u64* seq, u32* codes, u32 nseq, u8* dst, u32 cap, ZeBlkMeta& M) {
+	ZeEnt& e = W->e;
+	u32 lane = zg_lane();
+	u8* end = dst + cap;
+	u8* p = dst;
 	if (p + 4 > end) return 0;
 	if (nseq == 0) {
 		if (lane == 0) *p = 0;
-		p++;
-		return (u32)(p - dst);
+		return 1;
 	}
 	if (lane == 0) {
 		if (nseq < 128) p[0] = (u8)nseq;
@@ -1104,9 +1134,9 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 	__syncwarp();
 	u32 mx_ll = 0, mx_ml = 0, mx_of = 0;
 	for (u32 i = lane; i < nseq; i += 32) {
-		u64 q = S->seq[i];
+		u64 q = seq[i];
 		u32 lc = ze_ll_code(ZE_SEQ_LL(q)), mc = ze_ml_code(ZE_SEQ_ML(q) - 3), oc = zs_highbit(ZE_SEQ_OF(q));
-		S->codes[i] = lc | (mc << 8) | (oc << 16);
+		codes[i] = lc | (mc << 8) | (oc << 16);
 		atomicAdd(&e.hist3[0][lc], 1u);
 		atomicAdd(&e.hist3[1][mc], 1u);
 		atomicAdd(&e.hist3[2][oc], 1u);
@@ -1119,10 +1149,9 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 	mx_of = zg_warp_max(mx_of);
 	__syncwarp();
 	ZeCT ct3[3];  // LL, ML, OF
-	u32 bs_off;
 	{
 		u8* q = p + 1;  // after the modes byte
-		ZeCT pd_ll{P->st_ll, P->dnb_ll, P->dfs_ll, 6}, pd_ml{P->st_ml, P->dnb_ml, P->dfs_ml, 6}, pd_of{P->st_of, P->dnb_of, P->dfs_of, 5};
+		ZeCT pd_ll{P->st_ll, P->tt_ll, 6}, pd_ml{P->st_ml, P->tt_ml, 6}, pd_of{P->st_of, P->tt_of, 5};
 		u32 m_ll = ze_seq_table(W, pd_ll, 0, e.hist3[0], nseq, mx_ll, ZS_LL_MAXLOG, 35, q, end, ct3[0]);
 		if (m_ll == 0xff) return 0;
 		u32 m_of = ze_seq_table(W, pd_of, 2, e.hist3[2], nseq, mx_of, ZS_OF_MAXLOG, 28, q, end, ct3[2]);
@@ -1130,66 +1159,94 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 		u32 m_ml = ze_seq_table(W, pd_ml, 1, e.hist3[1], nseq, mx_ml, ZS_ML_MAXLOG, 52, q, end, ct3[1]);
 		if (m_ml == 0xff) return 0;
 		if (lane == 0) *p = (u8)((m_ll << 6) | (m_of << 4) | (m_ml << 2));
-		bs_off = (u32)(q - dst);
+		p = q;
 	}
-	u32 logs[3] = {ct3[0].log, ct3[1].log, ct3[2].log};
+	M.logs = ct3[0].log | (ct3[1].log << 8) | (ct3[2].log << 16);
 	__syncwarp();
-	// Phase 1: the three FSE state chains are independent of each other -> lanes 0,1,2 walk one
-	// each (last sequence first, libzstd's ZSTD_encodeSequences order), leaving per sequence the
-	// bits that chain emits (value | nbBits << 12).  Four steps per trip: the symbol codes and
-	// their table rows are fetched up front, only the state look-ups are serial.
+	return (u32)(p - dst);
+}
+
+// The three FSE state chains of one block (last sequence first, libzstd's ZSTD_encodeSequences
+// order) are independent of each other: lanes 0,1,2 walk one each over the tables in shared memory,
+// leaving per sequence the bits the chain emits as a 16-bit field (value | nbBits << 12) of a 64-bit
+// word: LL | ML << 16 | OF << 32.  Four steps per trip: the symbol codes and their table rows are
+// fetched up front, only the state look-ups are serial.  All lanes call; fills M.fin.
+ZG_DEV void ze_sequences_chains(ZeWarp* W, const u32* codes, u16* stb16, ZeBlkMeta& M) {
+	ZeEnt& e = W->e;
+	u32 lane = zg_lane();
+	u32 nseq = M.nseq;
 	if (lane < 3) {
-		u32 t = lane, sh = 8 * lane;  // codes = ll | ml << 8 | of << 16; table index 0 LL, 1 ML, 2 OF
-		ZeCT ct = lane == 0 ? ct3[0] : lane == 1 ? ct3[1] : ct3[2];
-		u16* out = S->stb[t];
-		u32 state = ze_fse_init_state(ct, (S->codes[nseq - 1] >> sh) & 0xff);
-		out[nseq - 1] = 0;
+		u32 sh = 8 * lane;  // codes = ll | ml << 8 | of << 16; table index 0 LL, 1 ML, 2 OF
+		const u16* st = e.st[lane];
+		const ZeSymTT* tt = e.tt[lane];
+		u32 log = (M.logs >> sh) & 0xff;
+		u16* out = stb16 + lane;  // stride 4
+		ZeCT ct{e.st[lane], e.tt[lane], log};
+		u32 state = ze_fse_init_state(ct, (codes[nseq - 1] >> sh) & 0xff);
+		out[4 * (nseq - 1)] = 0;
 		u32 i = nseq - 1;
-		while (i >= 4) {
-			u32 d[4];
-			i32 f[4];
+		u32 c4[4] = {0, 0, 0, 0};
+		if (i >= 4) {
 			ZG_UNROLL
-			for (int k = 0; k < 4; k++) {
-				u32 code = (S->codes[i - 1 - k] >> sh) & 0xff;
-				d[k] = ct.dnb[code];
-				f[k] = ct.dfs[code];
+			for (int k = 0; k < 4; k++) c4[k] = codes[i - 1 - k];
+		}
+		while (i >= 4) {
+			ZeSymTT r[4];
+			ZG_UNROLL
+			for (int k = 0; k < 4; k++) r[k] = tt[(c4[k] >> sh) & 0xff];
+			if (i >= 8) {  // the next trip's codes are on their way while this trip's states resolve
+				ZG_UNROLL
+				for (int k = 0; k < 4; k++) c4[k] = codes[i - 5 - k];
 			}
 			ZG_UNROLL
 			for (int k = 0; k < 4; k++) {
-				u32 nb = (state + d[k]) >> 16;
-				out[i - 1 - k] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-				state = ct.st[(state >> nb) + f[k]];
+				u32 nb = (state + r[k].dnb) >> 16;
+				out[4 * (i - 1 - k)] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+				state = st[(state >> nb) + r[k].dfs];
 			}
 			i -= 4;
 		}
 		while (i-- > 0) {
-			u32 code = (S->codes[i] >> sh) & 0xff;
-			u32 nb = (state + ct.dnb[code]) >> 16;
-			out[i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-			state = ct.st[(state >> nb) + ct.dfs[code]];
+			ZeSymTT r = tt[(codes[i] >> sh) & 0xff];
+			u32 nb = (state + r.dnb) >> 16;
+			out[4 * i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+			state = st[(state >> nb) + r.dfs];
 		}
-		W->misc[8 + t] = state & ((1u << ct.log) - 1u);
+		W->misc[8 + lane] = state & ((1u << log) - 1u);
 	}
 	__syncwarp();
-	// Phase 2: every lane assembles one sequence's bit field (<= 89 bits: OF,ML,LL state bits then
-	// LL,ML,OF extra bits), a warp scan places it, and the fields are OR-ed into a shared window.
+	M.fin[0] = W->misc[8];
+	M.fin[1] = W->misc[9];
+	M.fin[2] = W->misc[10];
+	__syncwarp();
+}
+
+// K3b3: the sequence bitstream of one block into dst[0..cap).  Every lane assembles one sequence's
+// bit field (<= 89 bits: OF,ML,LL state bits then LL,ML,OF extra bits), a warp scan places it, and
+// the fields are OR-ed into a shared window.  Returns the bytes written, 0 when it does not fit.
+ZG_DEV u32 ze_sequences_pack(ZeWarp* W, const u64* seq, const u32* codes, const u64* stb, const ZeBlkMeta& M, u8* dst, u32 cap) {
+	ZeEnt& e = W->e;
+	u32 lane = zg_lane();
+	u32 nseq = M.nseq;
+	u32 logs[3] = {M.logs & 0xff, (M.logs >> 8) & 0xff, M.logs >> 16};
 	ZePack pk;
-	ze_pack_init(pk, e.window, dst + bs_off, cap - bs_off);
+	ze_pack_init(pk, e.window, dst, cap);
 	for (u32 hi = nseq; hi > 0; hi -= zg_min<u32>(hi, 32u)) {
 		u64 lo64 = 0;
 		u32 hi32 = 0, nb = 0;
 		if (lane < hi) {
 			u32 i = hi - 1 - lane;
-			u32 c = S->codes[i];
+			u32 c = codes[i];
 			u32 lc = c & 0xff, mc = (c >> 8) & 0xff, oc = c >> 16;
-			u32 a = S->stb[2][i], b = S->stb[1][i], d = S->stb[0][i];
+			u64 sb = stb[i];
+			u32 a = (u32)(sb >> 32) & 0xffff, b = (u32)(sb >> 16) & 0xffff, d = (u32)sb & 0xffff;
 			lo64 = a & 0xfff;
 			nb = a >> 12;
 			lo64 |= (u64)(b & 0xfff) << nb;
 			nb += b >> 12;
 			lo64 |= (u64)(d & 0xfff) << nb;
 			nb += d >> 12;
-			u64 q = S->seq[i];
+			u64 q = seq[i];
 			lo64 |= (u64)(ZE_SEQ_LL(q) - ZS_LL_BASE[lc]) << nb;
 			nb += ZS_LL_BITS[lc];
 			lo64 |= (u64)(ZE_SEQ_ML(q) - ZS_ML_BASE[mc]) << nb;
@@ -1206,11 +1263,11 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 		u64 lo64 = 0;
 		u32 nb = 0;
 		if (lane == 0) {
-			lo64 = W->misc[9];
+			lo64 = M.fin[1];
 			nb = logs[1];
-			lo64 |= (u64)W->misc[10] << nb;
+			lo64 |= (u64)M.fin[2] << nb;
 			nb += logs[2];
-			lo64 |= (u64)W->misc[8] << nb;
+			lo64 |= (u64)M.fin[0] << nb;
 			nb += logs[0];
 			lo64 |= (u64)1 << nb;
 			nb += 1;
@@ -1219,86 +1276,231 @@ ZG_DEV u32 ze_entropy_block(ZeWarp* W, ZePredef* P, ZeScratch* S, u32 nseq, u32 
 	}
 	u32 bytes = ze_pack_finish(pk);
 	__syncwarp();
-	return pk.ovf ? 0 : bs_off + bytes;
+	return pk.ovf ? 0 : bytes;
 }
 
 struct ZeParams {
 	u32 lazy;      // 1: one-step lazy parse (levels >= 3)
 	u32 window;    // reserved
 };
+// everything the three kernels need to find a block and its staging
+struct ZeJob {
+	const u8* blob;
+	const u64* file_off;
+	const u64* comp_off;
+	const u64* file_len;
+	const u32* ulist;
+	const u64* blk_base;
+	u32 nuniq;
+	u64 nblocks;
+	u8* comp;          // encoded-block staging blob, laid out like the unique inputs
+	u32* blk_csize;
+	ZeBlkMeta* meta;   // [nblocks]
+	u64* seqbuf;       // chunk staging: sequences (8 B per 4 input bytes)
+	u8* litbuf;        // chunk staging: literals (1 B per input byte)
+	u32* codebuf;      // chunk staging: sequence codes (4 B per 4 input bytes)
+	u64* stbbuf;       // chunk staging: FSE state bits (8 B per 4 input bytes)
+	const u64* bounds; // [nchunks + 1] first block of every chunk
+	u64 chunk_bytes;
+};
+struct ZeBlk {
+	u32 f;         // file
+	u32 n;         // block bytes
+	u64 j;         // block index inside the file
+	u64 soff;      // offset of the block in the staging blob
+};
+// block -> (unique file, block index): last u with blk_base[u] <= b
+ZG_DEV ZeBlk ze_locate(const ZeJob& J, u64 b) {
+	u32 lo = 0, hi = J.nuniq - 1;
+	while (lo < hi) {
+		u32 mid = (lo + hi + 1) >> 1;
+		if (J.blk_base[mid] <= b) lo = mid;
+		else hi = mid - 1;
+	}
+	ZeBlk B;
+	B.f = J.ulist[lo];
+	B.j = b - J.blk_base[lo];
+	u64 flen = J.file_len[B.f];
+	u64 boff = B.j * ZS_BLOCK_MAX;
+	B.n = (u32)zg_min<u64>(ZS_BLOCK_MAX, flen - zg_min<u64>(flen, boff));
+	B.soff = J.comp_off[B.f] + boff;
+	return B;
+}
+// next block of chunk k from the kernel's queue; false when the chunk is exhausted
+ZG_DEV bool ze_next_block(const ZeJob& J, u32 chunk, u32* queue, u64& b) {
+	u32 t = 0;
+	if (zg_lane() == 0) t = atomicAdd(queue, 1u);
+	t = __shfl_sync(ZG_FULL, t, 0);
+	b = J.bounds[chunk] + t;
+	return b < J.bounds[chunk + 1];
+}
 
-__global__ void __launch_bounds__(ZE_WARPS * 32, ZE_MIN_CTAS)
-k_zstd_encode_blocks(const u8* __restrict__ blob, const u64* __restrict__ file_off, const u64* __restrict__ comp_off,
-                     const u64* __restrict__ file_len,
-                     const u32* __restrict__ ulist, const u64* __restrict__ blk_base, u32 nuniq, u64 nblocks, u8* comp,
-                     u32* __restrict__ blk_csize, ZeScratch* scratch, u32* queue, ZeParams prm) {
+// first block of every chunk: chunk k holds the blocks whose staging offset is in [k, k+1) * chunk_bytes
+__global__ void __launch_bounds__(128) k_ze_chunk_bounds(ZeJob J, u32 nchunks, u64* bounds) {
+	u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > nchunks) return;
+	if (k == nchunks) {
+		bounds[k] = J.nblocks;
+		return;
+	}
+	u64 want = (u64)k * J.chunk_bytes;
+	u64 lo = 0, hi = J.nblocks;  // first block with soff >= want
+	while (lo < hi) {
+		u64 mid = (lo + hi) >> 1;
+		if (ze_locate(J, mid).soff >= want) hi = mid;
+		else lo = mid + 1;
+	}
+	bounds[k] = lo;
+}
+
+// K2
+__global__ void __launch_bounds__(ZE_WARPS * 32, ZE_MIN_CTAS) k_zstd_match_blocks(ZeJob J, u32 chunk, u32* queue, ZeParams prm) {
+	ZG_DYN_SMEM(ZeMatchWarp, sm);
+	ZeMatchWarp* W = &sm[threadIdx.x >> 5];
+	u32 lane = threadIdx.x & 31;
+	u64 b;
+	while (ze_next_block(J, chunk, queue, b)) {
+		ZeBlk B = ze_locate(J, b);
+		u64 rel = B.soff - (u64)chunk * J.chunk_bytes;
+		u64* seq = J.seqbuf + (rel >> 2);
+		u8* lit = J.litbuf + rel;
+		u32 nseq = ZE_RAW, nlit = 0;
+		if (B.n >= 16) {
+			nseq = ze_match_block(W, seq, lit, J.blob + J.file_off[B.f] + B.j * ZS_BLOCK_MAX, B.n, prm.lazy, &nlit);
+			__syncwarp();
+			// later blocks of a frame are encoded independently of their predecessors: unknown history
+			if (!ze_assign_repcodes(W, seq, nseq, B.j == 0)) nseq = ZE_RAW;
+		}
+		__syncwarp();
+		if (lane == 0) {
+			J.meta[b].nseq = nseq;
+			J.meta[b].nlit = nlit;
+		}
+	}
+}
+
+// K3a
+__global__ void __launch_bounds__(ZE_WARPS * 32, ZE_ENT_CTAS) k_zstd_literals(ZeJob J, u32 chunk, u32* queue) {
+	ZG_DYN_SMEM(ZeWarp, sm);
+	ZeWarp* W = &sm[threadIdx.x >> 5];
+	u32 lane = threadIdx.x & 31;
+	u64 b;
+	while (ze_next_block(J, chunk, queue, b)) {
+		ZeBlkMeta m = J.meta[b];
+		u32 litsec = 0;
+		if (m.nseq != ZE_RAW) {
+			ZeBlk B = ze_locate(J, b);
+			u64 rel = B.soff - (u64)chunk * J.chunk_bytes;
+			litsec = ze_literals_section(W, J.litbuf + rel, m.nlit, J.comp + B.soff, B.n - 1);
+		}
+		__syncwarp();
+		if (lane == 0) J.meta[b].litsec = litsec;
+	}
+}
+
+// K3b
+__global__ void __launch_bounds__(ZE_WARPS * 32, ZE_ENT_CTAS) k_zstd_sequences(ZeJob J, u32 chunk, u32* queue) {
 	ZG_DYN_SMEM(ZeWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZeWarp* W = &sm[warp];
 	ZePredef* P = (ZePredef*)(sm + ZE_WARPS);
-	ZeScratch* S = scratch + (size_t)(blockIdx.x * ZE_WARPS + warp);
 	if (threadIdx.x == 0) {  // the predefined compression tables, once per (persistent) CTA
-		ZeEnt& e = W->u.e;
-		ze_fse_build_ctable(ZeCT{P->st_ll, P->dnb_ll, P->dfs_ll, 6}, ZS_LL_DEFAULT_NORM, 35, e.tsym, e.cumul);
-		ze_fse_build_ctable(ZeCT{P->st_ml, P->dnb_ml, P->dfs_ml, 6}, ZS_ML_DEFAULT_NORM, 52, e.tsym, e.cumul);
-		ze_fse_build_ctable(ZeCT{P->st_of, P->dnb_of, P->dfs_of, 5}, ZS_OF_DEFAULT_NORM, 28, e.tsym, e.cumul);
+		ZeEnt& e = W->e;
+		ze_fse_build_ctable(ZeCT{P->st_ll, P->tt_ll, 6}, ZS_LL_DEFAULT_NORM, 35, e.tsym, e.cumul);
+		ze_fse_build_ctable(ZeCT{P->st_ml, P->tt_ml, 6}, ZS_ML_DEFAULT_NORM, 52, e.tsym, e.cumul);
+		ze_fse_build_ctable(ZeCT{P->st_of, P->tt_of, 5}, ZS_OF_DEFAULT_NORM, 28, e.tsym, e.cumul);
 	}
 	__syncthreads();
-	for (;;) {
-		u32 b = 0;
-		if (lane == 0) b = atomicAdd(queue, 1u);
-		b = __shfl_sync(ZG_FULL, b, 0);
-		if (b >= nblocks) break;
-		// block -> (unique file, block index): last u with blk_base[u] <= b
-		u32 lo = 0, hi = nuniq - 1;
-		while (lo < hi) {
-			u32 mid = (lo + hi + 1) >> 1;
-			if (blk_base[mid] <= b) lo = mid;
-			else hi = mid - 1;
-		}
-		u32 f = ulist[lo];
-		u64 j = b - blk_base[lo];
-		u64 flen = file_len[f];
-		u64 boff = j * ZS_BLOCK_MAX;
-		u32 n = (u32)zg_min<u64>(ZS_BLOCK_MAX, flen - zg_min<u64>(flen, boff));
-		const u8* src = blob + file_off[f] + boff;
-		u8* dst = comp + comp_off[f] + boff;
+	u64 b;
+	while (ze_next_block(J, chunk, queue, b)) {
+		ZeBlkMeta m = J.meta[b];
+		ZeBlk B = ze_locate(J, b);
 		u32 csize = 0;
-		if (n >= 16) {
-			u32 nlit = 0;
-			u32 nseq = ze_match_block(W, S, src, n, prm.lazy, &nlit);
-			__syncwarp();
-			// later blocks of a frame are encoded independently of their predecessors: unknown history
-			if (ze_assign_repcodes(W, S, nseq, j == 0))
-				csize = ze_entropy_block(W, P, S, nseq, nlit, dst, n - 1);
-			__syncwarp();
+		if (m.nseq != ZE_RAW && m.litsec) {
+			u64 rel = B.soff - (u64)chunk * J.chunk_bytes;
+			const u64* seq = J.seqbuf + (rel >> 2);
+			u32* codes = J.codebuf + (rel >> 2);
+			u64* stb = J.stbbuf + (rel >> 2);
+			u8* dst = J.comp + B.soff + m.litsec;
+			u32 cap = B.n - 1 - m.litsec;
+			u32 hdr = ze_sequences_tables(W, P, seq, codes, m.nseq, dst, cap, m);
+			if (hdr && m.nseq == 0) {
+				csize = m.litsec + hdr;
+			} else if (hdr) {
+				__syncwarp();
+				ze_sequences_chains(W, codes, (u16*)stb, m);
+				u32 sz = ze_sequences_pack(W, seq, codes, stb, m, dst + hdr, cap - hdr);
+				if (sz) csize = m.litsec + hdr + sz;
+			}
 		}
 		__syncwarp();
-		if (lane == 0) blk_csize[b] = csize ? csize : (ZE_RAW | n);
+		if (lane == 0) J.blk_csize[b] = csize ? csize : (ZE_RAW | B.n);
 	}
 }
 
+// input bytes per chunk; tests shrink it to exercise the multi-chunk path (multiple of 16)
+static u64 g_ze_chunk_bytes = ZE_CHUNK_BYTES;
+extern "C" void zg_internal_set_encode_chunk_bytes(u64 v) { g_ze_chunk_bytes = v ? (v + 15) & ~(u64)15 : ZE_CHUNK_BYTES; }
+
 size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
-                          const u32* ulist,
-                          const u64* blk_base, u32 nuniq, u64 nblocks, u8* comp, u32* blk_csize, int level) {
+                          const u32* ulist, const u64* blk_base, u32 nuniq, u64 nblocks, u64 comp_bytes, u8* comp, u32* blk_csize,
+                          int level) {
 	if (nblocks == 0) return 0;
-	u32 grid = (u32)zg_min<u64>((nblocks + ZE_WARPS - 1) / ZE_WARPS, (u64)zg_sm_count() * ZE_MIN_CTAS);
-	if (w.scratch.reserve((size_t)grid * ZE_WARPS * sizeof(ZeScratch)) || w.queue.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
-	cudaMemsetAsync(w.queue.p, 0, 16, s);
+	const u64 chunk_bytes = g_ze_chunk_bytes;
+	u32 nchunks = (u32)((comp_bytes + chunk_bytes - 1) / chunk_bytes);
+	if (nchunks == 0) nchunks = 1;
+	u64 span = zg_min<u64>(comp_bytes, chunk_bytes) + ZS_BLOCK_MAX + 64;  // a chunk's last block may stick out
+	u32 sms = (u32)zg_sm_count();
+	u32 grid_m = (u32)zg_min<u64>((nblocks + ZE_WARPS - 1) / ZE_WARPS, (u64)sms * ZE_MIN_CTAS);
+	u32 grid_e = (u32)zg_min<u64>((nblocks + ZE_WARPS - 1) / ZE_WARPS, (u64)sms * ZE_ENT_CTAS);
+	size_t qbytes = (size_t)nchunks * ZE_NQ * 4 + 16;
+	if (w.queue.reserve(qbytes) || w.meta.reserve(nblocks * sizeof(ZeBlkMeta)) || w.seqbuf.reserve(span * 2) || w.litbuf.reserve(span) ||
+	    w.codebuf.reserve(span) || w.stbbuf.reserve(span * 2) || w.bounds.reserve(((size_t)nchunks + 1) * 8))
+		return ZG_ERR(ZG_error_memory_allocation);
+	cudaMemsetAsync(w.queue.p, 0, qbytes, s);
 	ZeParams prm;
 	prm.lazy = level >= 3 ? 1 : 0;
 	prm.window = 0;
-	size_t smem = sizeof(ZeWarp) * ZE_WARPS + sizeof(ZePredef);
+	ZeJob J;
+	J.blob = blob;
+	J.file_off = file_off;
+	J.comp_off = comp_off;
+	J.file_len = file_len;
+	J.ulist = ulist;
+	J.blk_base = blk_base;
+	J.nuniq = nuniq;
+	J.nblocks = nblocks;
+	J.comp = comp;
+	J.blk_csize = blk_csize;
+	J.meta = w.meta.as<ZeBlkMeta>();
+	J.seqbuf = w.seqbuf.as<u64>();
+	J.litbuf = w.litbuf.as<u8>();
+	J.codebuf = w.codebuf.as<u32>();
+	J.stbbuf = w.stbbuf.as<u64>();
+	J.bounds = w.bounds.as<u64>();
+	J.chunk_bytes = chunk_bytes;
+	size_t smem_m = sizeof(ZeMatchWarp) * ZE_WARPS;
+	size_t smem_l = sizeof(ZeWarp) * ZE_WARPS;
+	size_t smem_q = sizeof(ZeWarp) * ZE_WARPS + sizeof(ZePredef);
 	static bool attr_set = false;
 	if (!attr_set) {
-		if (cudaFuncSetAttribute(k_zstd_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+		if (cudaFuncSetAttribute(k_zstd_match_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess ||
+		    cudaFuncSetAttribute(k_zstd_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess ||
+		    cudaFuncSetAttribute(k_zstd_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q) != cudaSuccess)
 			return ZG_ERR(ZG_error_device);
 		attr_set = true;
 	}
 	zg_prof_begin(ZG_K_ENCODE, s);
-	ZG_LAUNCH(k_zstd_encode_blocks, grid, ZE_WARPS * 32, smem, s, blob, file_off, comp_off, file_len, ulist, blk_base, nuniq, nblocks, comp,
-	          blk_csize, w.scratch.as<ZeScratch>(), w.queue.as<u32>(), prm);
-	zg_prof_end(ZG_K_ENCODE, s);
+	ZG_LAUNCH(k_ze_chunk_bounds, (nchunks + 128) / 128, 128, 0, s, J, nchunks, w.bounds.as<u64>());
 	ZG_COUNT_LAUNCH();
+	u32* q = w.queue.as<u32>();
+	for (u32 k = 0; k < nchunks; k++) {
+		u32* qk = q + (size_t)k * ZE_NQ;
+		ZG_LAUNCH(k_zstd_match_blocks, grid_m, ZE_WARPS * 32, smem_m, s, J, k, qk + 0, prm);
+		ZG_LAUNCH(k_zstd_literals, grid_e, ZE_WARPS * 32, smem_l, s, J, k, qk + 1);
+		ZG_LAUNCH(k_zstd_sequences, grid_e, ZE_WARPS * 32, smem_q, s, J, k, qk + 2);
+		g_zg_launches += 3;
+	}
+	zg_prof_end(ZG_K_ENCODE, s);
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
 }
