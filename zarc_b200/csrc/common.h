@@ -57,6 +57,7 @@ int zg_sm_count();
 // ---- blake3.cu ----
 struct ZgB3Work {
 	ZgBuf big;     // u64 pairs {file idx, len}
+	ZgBuf med;     // u32 indices of files above 64 chunks
 	ZgBuf ctr;     // u32 counters
 	ZgBuf base;    // u64 group prefix per big file
 	ZgBuf nodes;   // level-5 chaining values of big files
