@@ -115,3 +115,37 @@ def test_pack_batch_capacity_error(emu):
     r = pack_batch(emu, c, [rand(5000, 3)], cap=100)
     assert emu.zg_get_error_code(r["rc"]) == 70
     emu.zg_cctx_free(c)
+
+
+def test_sliced_host_api_and_chunked_encoder_equal_one_shot(emu):
+    """zg_pack_batch/zg_unpack_batch cut a batch into double-buffered slices and the encoder cuts it into
+    chunks: with tiny slice/chunk sizes (dedup pairs and a multi-block file straddling the cuts) the
+    archive bytes, answers and restored files must equal the unsliced run."""
+    import ctypes as C
+
+    from zarc_b200 import corpus
+
+    c = corpus.c2_source_tree(total_bytes=500_000, seed=11)
+    blob = corpus.materialise_host(emu, c)
+    files = [bytes(blob[int(o) : int(o) + int(l)]) for o, l in zip(c.off, c.len)]
+    files += [files[1], files[0], bytes(blob[:150_000]) * 2, files[5], b"", b"x"]
+    results = []
+    try:
+        for slice_bytes, chunk_bytes in ((0, 0), (70_000, 0), (0, 4096), (33_000, 65536)):
+            emu.dll.zg_internal_set_slice_bytes(C.c_uint64(slice_bytes))
+            emu.dll.zg_internal_set_encode_chunk_bytes(C.c_uint64(chunk_bytes))
+            cctx = emu.zg_cctx_create()
+            emu.check(emu.zg_cctx_init(cctx, 3))
+            emu.check(emu.zg_cctx_set_parameter(cctx, 201, 1))
+            emu.check(emu.zg_cctx_reset_archive(cctx, 12))
+            r = pack_batch(emu, cctx, files)
+            emu.zg_cctx_free(cctx)
+            assert r["rc"] == 0
+            frames = [bytes(r["frames"][o - 12 : o - 12 + l]) for o, l in zip(r["off"], r["len"])]
+            outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], r["digests"])
+            assert rc == 0 and outs == files and all(ok)
+            results.append((bytes(r["frames"]), r["digests"], r["first"], r["off"], r["len"]))
+    finally:
+        emu.dll.zg_internal_set_slice_bytes(C.c_uint64(0))
+        emu.dll.zg_internal_set_encode_chunk_bytes(C.c_uint64(0))
+    assert all(x == results[0] for x in results[1:])

@@ -141,7 +141,7 @@ def main():
         best, med = timeit(run_pack, iters=3, warmup=1)
         lib.zg_profile_enable(0)
         import ctypes as C
-        for k, name in enumerate(["blake3", "encode", "decode", "assemble", "xxh64", "dedup"]):
+        for k, name in enumerate(["blake3", "encode", "decode", "assemble", "xxh64", "dedup", "match", "literals", "sequences"]):
             ms, cnt = C.c_double(0), C.c_uint64(0)
             lib.zg_profile_read(k, C.byref(ms), C.byref(cnt))
             if cnt.value:

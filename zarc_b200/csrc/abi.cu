@@ -7,6 +7,8 @@
 #include <string.h>
 
 uint64_t g_zg_launches = 0;
+uint64_t g_zg_slice_bytes = 1024ull << 20;
+extern "C" void zg_internal_set_slice_bytes(uint64_t v) { g_zg_slice_bytes = v ? v : (1024ull << 20); }
 
 static int g_dev_count = -2;
 static int g_sm_count = 0;
@@ -91,8 +93,14 @@ struct zg_dctx {
 	ZgZdWork zd;
 	ZgB3Work b3;
 	ZgBuf status, produced, cksums, got_digests, first, tiles, packed_off;
-	// host-API staging
-	ZgBuf d_archive, d_meta, d_out, d_digests, d_ok;
+	// host-API staging: two stages, so that the copies of one slice overlap the kernels of another
+	struct Stage {
+		ZgBuf d_archive, d_meta, d_out, d_digests, d_ok;
+		ZgHostBuf h_small;
+		cudaEvent_t in_done = nullptr, out_done = nullptr;
+	} hstage[2];
+	cudaStream_t s_in = nullptr, s_out = nullptr;
+	ZgBuf d_archive, d_out, d_meta;  // one-shot / streaming paths
 	ZgHostBuf h_first, h_small;
 	// streaming state (zg_decompress_stream)
 	std::vector<uint8_t> in_acc, out_acc;
@@ -316,8 +324,16 @@ void zg_dctx_free(zg_dctx* d) {
 	d->zd.queue.release();
 	zg_b3work_free(d->b3);
 	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->d_archive,
-	                 &d->d_meta, &d->d_out, &d->d_digests, &d->d_ok})
+	                 &d->d_meta, &d->d_out})
 		b->release();
+	for (auto& st : d->hstage) {
+		for (ZgBuf* b : {&st.d_archive, &st.d_meta, &st.d_out, &st.d_digests, &st.d_ok}) b->release();
+		st.h_small.release();
+		if (st.in_done) cudaEventDestroy(st.in_done);
+		if (st.out_done) cudaEventDestroy(st.out_done);
+	}
+	if (d->s_in) cudaStreamDestroy(d->s_in);
+	if (d->s_out) cudaStreamDestroy(d->s_out);
 	d->h_first.release();
 	d->h_small.release();
 	if (d->own_stream) cudaStreamDestroy(d->stream);
@@ -351,6 +367,8 @@ size_t zg_unpack_batch_dev(zg_dctx* d, const uint8_t* archive, uint64_t archive_
 	return unpack_core(d, archive, archive_len, n, off, len, ulen, digests, out, out_cap, out_off, ok, status);
 }
 
+// Host-buffer unpack, sliced and double-buffered like pack_host (abi_pack.cu): the archive bytes of
+// slice k+1 go up and the restored files of slice k-1 come down while slice k decodes.
 size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len, uint64_t n, const uint64_t* off,
                        const uint64_t* len, const uint64_t* ulen, const uint8_t* digests, uint8_t* out, uint64_t out_cap,
                        const uint64_t* out_off, uint8_t* ok, uint32_t* status) {
@@ -359,72 +377,140 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 	if (n == 0) return 0;
 	if (!out) return ZG_ERR(ZG_error_dstBuffer_null);
 	cudaStream_t s = d->stream;
-	// bookkeeping on offsets: the archive span this batch touches, and the output layout
-	u64 lo = ~0ull, hi = 0, total = 0;
+	if (!d->s_in) {
+		ZG_CUDA(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+		ZG_CUDA(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+		for (auto& st : d->hstage) {
+			ZG_CUDA(cudaEventCreateWithFlags(&st.in_done, cudaEventDisableTiming));
+			ZG_CUDA(cudaEventCreateWithFlags(&st.out_done, cudaEventDisableTiming));
+		}
+	}
+	// bookkeeping on offsets: is the output the dense concatenation (then it can be sliced)?
+	u64 total = 0;
 	bool dense = true;
 	for (u64 k = 0; k < n; k++) {
 		if (off[k] > archive_len || len[k] > archive_len - off[k]) return ZG_ERR(ZG_error_srcSize_wrong);
-		lo = off[k] < lo ? off[k] : lo;
-		hi = off[k] + len[k] > hi ? off[k] + len[k] : hi;
 		if (out_off && out_off[k] != total) dense = false;
 		total += ulen[k];
 	}
-	u64 out_lo = 0, out_hi = total;
-	if (out_off && !dense) {
-		out_lo = ~0ull;
-		out_hi = 0;
+	if (dense && total > out_cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
+	struct Slice {
+		u64 i0, i1, lo, hi, obase, obytes, olo, ohi;
+	};
+	std::vector<Slice> sl;
+	{
+		Slice cur{0, 0, ~0ull, 0, 0, 0, ~0ull, 0};
+		u64 spans = 0, cbytes = 0, acc = 0;
 		for (u64 k = 0; k < n; k++) {
-			if (out_off[k] > out_cap || ulen[k] > out_cap - out_off[k]) return ZG_ERR(ZG_error_dstSize_tooSmall);
-			out_lo = out_off[k] < out_lo ? out_off[k] : out_lo;
-			out_hi = out_off[k] + ulen[k] > out_hi ? out_off[k] + ulen[k] : out_hi;
+			cur.lo = off[k] < cur.lo ? off[k] : cur.lo;
+			cur.hi = off[k] + len[k] > cur.hi ? off[k] + len[k] : cur.hi;
+			cur.obytes += ulen[k];
+			cbytes += len[k];
+			if (!dense) {
+				if (out_off[k] > out_cap || ulen[k] > out_cap - out_off[k]) return ZG_ERR(ZG_error_dstSize_tooSmall);
+				cur.olo = out_off[k] < cur.olo ? out_off[k] : cur.olo;
+				cur.ohi = out_off[k] + ulen[k] > cur.ohi ? out_off[k] + ulen[k] : cur.ohi;
+			}
+			acc += ulen[k];
+			if ((dense && cur.obytes >= g_zg_slice_bytes) || k + 1 == n) {
+				cur.i1 = k + 1;
+				if (dense) {
+					cur.olo = cur.obase;
+					cur.ohi = cur.obase + cur.obytes;
+				}
+				sl.push_back(cur);
+				spans += cur.hi - cur.lo;
+				cur = Slice{k + 1, 0, ~0ull, 0, acc, 0, ~0ull, 0};
+			}
 		}
-	} else if (total > out_cap) {
-		return ZG_ERR(ZG_error_dstSize_tooSmall);
+		if (sl.size() > 1 && spans > 2 * cbytes + (64ull << 20)) {  // frames scattered over the archive: one slice
+			Slice all{0, n, ~0ull, 0, 0, total, 0, total};
+			for (u64 k = 0; k < n; k++) {
+				all.lo = off[k] < all.lo ? off[k] : all.lo;
+				all.hi = off[k] + len[k] > all.hi ? off[k] + len[k] : all.hi;
+			}
+			sl.assign(1, all);
+		}
 	}
-	u64 span = hi - lo, ospan = out_hi - out_lo;
-	// device arrays: off' (rebased), len, ulen, out_off' (rebased)
-	ZG_ALLOC(d->d_archive.reserve(span + 16));
-	ZG_ALLOC(d->d_meta.reserve(n * 32));
-	ZG_ALLOC(d->d_out.reserve(ospan + 16));
-	ZG_ALLOC(d->d_ok.reserve(n * 5));
-	ZG_ALLOC(d->h_small.reserve(n * 16));
-	u64* h_off = d->h_small.as<u64>();
-	u64* h_oo = h_off + n;
-	u64 acc = 0;
-	for (u64 k = 0; k < n; k++) {
-		h_off[k] = off[k] - lo;
-		h_oo[k] = (out_off && !dense) ? out_off[k] - out_lo : acc;
-		acc += ulen[k];
+	auto upload = [&](size_t k) -> size_t {
+		const Slice& q = sl[k];
+		auto& st = d->hstage[k & 1];
+		u64 m = q.i1 - q.i0, span = q.hi - q.lo, ospan = q.ohi - q.olo;
+		ZG_ALLOC(st.d_archive.reserve(span + 16));
+		ZG_ALLOC(st.d_meta.reserve(m * 32));
+		ZG_ALLOC(st.d_out.reserve(ospan + 16));
+		ZG_ALLOC(st.d_ok.reserve(m * 5 + 8));
+		ZG_ALLOC(st.h_small.reserve(m * 16));
+		u64* h_off = st.h_small.as<u64>();
+		u64* h_oo = h_off + m;
+		u64 acc = 0;
+		for (u64 i = 0; i < m; i++) {
+			h_off[i] = off[q.i0 + i] - q.lo;
+			h_oo[i] = dense ? acc : out_off[q.i0 + i] - q.olo;
+			acc += ulen[q.i0 + i];
+		}
+		ZG_CUDA(cudaStreamWaitEvent(d->s_in, st.out_done, 0));  // the stage's previous results have left
+		u64* dm = st.d_meta.as<u64>();
+		ZG_CUDA(cudaMemcpyAsync(st.d_archive.p, archive + q.lo, span, cudaMemcpyHostToDevice, d->s_in));
+		ZG_CUDA(cudaMemcpyAsync(dm, h_off, m * 8, cudaMemcpyHostToDevice, d->s_in));
+		ZG_CUDA(cudaMemcpyAsync(dm + m, len + q.i0, m * 8, cudaMemcpyHostToDevice, d->s_in));
+		ZG_CUDA(cudaMemcpyAsync(dm + 2 * m, ulen + q.i0, m * 8, cudaMemcpyHostToDevice, d->s_in));
+		ZG_CUDA(cudaMemcpyAsync(dm + 3 * m, h_oo, m * 8, cudaMemcpyHostToDevice, d->s_in));
+		if (digests && ok) {
+			ZG_ALLOC(st.d_digests.reserve(m * 32));
+			ZG_CUDA(cudaMemcpyAsync(st.d_digests.p, digests + 32 * q.i0, m * 32, cudaMemcpyHostToDevice, d->s_in));
+		}
+		ZG_CUDA(cudaEventRecord(st.in_done, d->s_in));
+		return 0;
+	};
+	size_t r = upload(0), first_err = 0;
+	for (size_t k = 0; k < sl.size() && !zg_is_error(r); k++) {
+		const Slice& q = sl[k];
+		auto& st = d->hstage[k & 1];
+		u64 m = q.i1 - q.i0, span = q.hi - q.lo, ospan = q.ohi - q.olo;
+		if (k + 1 < sl.size()) {
+			r = upload(k + 1);
+			if (zg_is_error(r)) break;
+		}
+		u64* dm = st.d_meta.as<u64>();
+		u8* d_dig = (digests && ok) ? st.d_digests.as<u8>() : nullptr;
+		u8* d_okp = st.d_ok.as<u8>();
+		u32* d_status = (u32*)(d_okp + ((m + 3) & ~(u64)3));
+		if (cudaStreamWaitEvent(s, st.in_done, 0) != cudaSuccess) {
+			r = ZG_ERR(ZG_error_device);
+			break;
+		}
+		size_t rk = unpack_core(d, st.d_archive.as<u8>(), span, m, dm, dm + m, dm + 2 * m, d_dig, st.d_out.as<u8>(), ospan, dm + 3 * m,
+		                        d_dig ? d_okp : nullptr, d_status);
+		if (zg_is_error(rk)) {
+			if (zg_get_error_code(rk) == ZG_error_device || zg_get_error_code(rk) == ZG_error_memory_allocation) {
+				r = rk;
+				break;
+			}
+			if (!first_err) first_err = rk;  // a frame failed: its status says which; the other frames are still delivered
+		}
+		cudaError_t e = cudaSuccess;
+		if (!dense) {
+			std::vector<u8> tmp(ospan);
+			e = cudaMemcpyAsync(tmp.data(), st.d_out.p, ospan, cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+			if (e == cudaSuccess)
+				for (u64 i = q.i0; i < q.i1; i++) memcpy(out + out_off[i], tmp.data() + (out_off[i] - q.olo), ulen[i]);
+		} else if (q.obytes) {
+			e = cudaMemcpyAsync(out + q.obase, st.d_out.p, q.obytes, cudaMemcpyDeviceToHost, d->s_out);
+		}
+		if (d_dig && e == cudaSuccess) e = cudaMemcpyAsync(ok + q.i0, d_okp, m, cudaMemcpyDeviceToHost, d->s_out);
+		if (status && e == cudaSuccess) e = cudaMemcpyAsync(status + q.i0, d_status, m * 4, cudaMemcpyDeviceToHost, d->s_out);
+		if (e == cudaSuccess) e = cudaEventRecord(st.out_done, d->s_out);
+		if (e != cudaSuccess) {
+			r = ZG_ERR(ZG_error_device);
+			break;
+		}
 	}
-	u64* m = d->d_meta.as<u64>();
-	ZG_CUDA(cudaMemcpyAsync(d->d_archive.p, archive + lo, span, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaMemcpyAsync(m, h_off, n * 8, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaMemcpyAsync(m + n, len, n * 8, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaMemcpyAsync(m + 2 * n, ulen, n * 8, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaMemcpyAsync(m + 3 * n, h_oo, n * 8, cudaMemcpyHostToDevice, s));
-	u8* d_dig = nullptr;
-	if (digests && ok) {
-		ZG_ALLOC(d->d_digests.reserve(n * 32));
-		d_dig = d->d_digests.as<u8>();
-		ZG_CUDA(cudaMemcpyAsync(d_dig, digests, n * 32, cudaMemcpyHostToDevice, s));
-	}
-	u8* d_okp = d->d_ok.as<u8>();
-	u32* d_status = (u32*)(d_okp + ((n + 3) & ~(u64)3));
-	size_t r = unpack_core(d, d->d_archive.as<u8>(), span, n, m, m + n, m + 2 * n, d_dig, d->d_out.as<u8>(), ospan, m + 3 * n,
-	                       d_dig ? d_okp : nullptr, d_status);
-	if (zg_is_error(r) && (zg_get_error_code(r) == ZG_error_device || zg_get_error_code(r) == ZG_error_memory_allocation)) return r;
-	if (out_off && !dense) {
-		std::vector<u8> tmp(ospan);
-		ZG_CUDA(cudaMemcpyAsync(tmp.data(), d->d_out.p, ospan, cudaMemcpyDeviceToHost, s));
-		ZG_CUDA(cudaStreamSynchronize(s));
-		for (u64 k = 0; k < n; k++) memcpy(out + out_off[k], tmp.data() + (out_off[k] - out_lo), ulen[k]);
-	} else {
-		ZG_CUDA(cudaMemcpyAsync(out, d->d_out.p, total, cudaMemcpyDeviceToHost, s));
-	}
-	if (d_dig) ZG_CUDA(cudaMemcpyAsync(ok, d_okp, n, cudaMemcpyDeviceToHost, s));
-	if (status) ZG_CUDA(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s));
-	ZG_CUDA(cudaStreamSynchronize(s));
-	return r;
+	cudaError_t e1 = cudaStreamSynchronize(d->s_in), e2 = cudaStreamSynchronize(d->s_out);
+	if (zg_is_error(r)) return r;
+	if (e1 != cudaSuccess || e2 != cudaSuccess) return ZG_ERR(ZG_error_device);
+	return first_err;
 }
 
 size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t n) {

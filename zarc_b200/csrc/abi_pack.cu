@@ -69,8 +69,13 @@ struct zg_cctx {
 	ZgBuf tiles, rep, isfirst64, nblk, clen, uidx, blkfirst, comp_off, ulist, blk_base, blk_csize, blk_out, blk_pos, frame_len_u,
 	    frame_off_u, xxh, comp, totals, first_tmp;
 	ZgHostBuf h;
-	// host-API staging
-	ZgBuf d_blob, d_meta, d_out_meta, d_frames;
+	// host-API staging: two stages, so that the copies of one slice overlap the kernels of another
+	struct Stage {
+		ZgBuf d_blob, d_meta, d_out_meta, d_frames;
+		ZgHostBuf h_meta;
+		cudaEvent_t in_done = nullptr, out_done = nullptr;
+	} stage[2];
+	cudaStream_t s_in = nullptr, s_out = nullptr;
 };
 
 static cudaError_t grow_keep(ZgBuf& b, size_t need, size_t keep, cudaStream_t s) {
@@ -205,9 +210,16 @@ void zg_cctx_free(zg_cctx* c) {
 	zg_b3work_free(c->b3);
 	c->ze.release();
 	for (ZgBuf* b : {&c->tiles, &c->rep, &c->isfirst64, &c->nblk, &c->clen, &c->uidx, &c->blkfirst, &c->comp_off, &c->ulist, &c->blk_base,
-	                 &c->blk_csize, &c->blk_out, &c->blk_pos, &c->frame_len_u, &c->frame_off_u, &c->xxh, &c->comp, &c->totals, &c->first_tmp,
-	                 &c->d_blob, &c->d_meta, &c->d_out_meta, &c->d_frames})
+	                 &c->blk_csize, &c->blk_out, &c->blk_pos, &c->frame_len_u, &c->frame_off_u, &c->xxh, &c->comp, &c->totals, &c->first_tmp})
 		b->release();
+	for (auto& st : c->stage) {
+		for (ZgBuf* b : {&st.d_blob, &st.d_meta, &st.d_out_meta, &st.d_frames}) b->release();
+		st.h_meta.release();
+		if (st.in_done) cudaEventDestroy(st.in_done);
+		if (st.out_done) cudaEventDestroy(st.out_done);
+	}
+	if (c->s_in) cudaStreamDestroy(c->s_in);
+	if (c->s_out) cudaStreamDestroy(c->s_out);
 	c->h.release();
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -290,43 +302,116 @@ size_t zg_pack_batch_dev(zg_cctx* c, const uint8_t* blob, const uint64_t* off, c
 	return pack_core(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes);
 }
 
+// Host-buffer pack.  The batch is cut into slices of about g_zg_slice_bytes of input (in file order) that
+// go through two staging sets: while the kernels of slice k run on the context's stream, slice k+1
+// is already on its way up (s_in) and the frames of slice k-1 are on their way down (s_out).  The
+// archive state (dedup map, running offset) carries from slice to slice exactly as it does from call
+// to call, so the results equal one pack_core over the whole batch.
 static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n,
                         uint8_t* digests, uint8_t* first, uint64_t* frame_off, uint64_t* frame_len, uint8_t* frames_out,
                         uint64_t frames_cap, uint64_t* frames_bytes) {
 	cudaStream_t s = c->stream;
 	if (frames_bytes) *frames_bytes = 0;
 	if (n == 0) return 0;
-	u64 lo = ~0ull, hi = 0;
-	for (u64 i = 0; i < n; i++) {
-		lo = off[i] < lo ? off[i] : lo;
-		hi = off[i] + len[i] > hi ? off[i] + len[i] : hi;
+	if (!c->s_in) {
+		ZG_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+		ZG_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+		for (auto& st : c->stage) {
+			ZG_CUDA(cudaEventCreateWithFlags(&st.in_done, cudaEventDisableTiming));
+			ZG_CUDA(cudaEventCreateWithFlags(&st.out_done, cudaEventDisableTiming));
+		}
 	}
-	u64 span = hi - lo;
-	ZG_ALLOC(c->d_blob.reserve(span + 64));
-	ZG_ALLOC(c->d_meta.reserve(n * 16));
-	ZG_ALLOC(c->d_out_meta.reserve(n * 49 + 64));
-	ZG_ALLOC(c->d_frames.reserve(frames_cap + 64));
-	std::vector<u64> rebased(n);
-	for (u64 i = 0; i < n; i++) rebased[i] = off[i] - lo;
-	u64* m = c->d_meta.as<u64>();
-	if (span) ZG_CUDA(cudaMemcpyAsync(c->d_blob.p, blob + lo, span, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaMemcpyAsync(m, rebased.data(), n * 8, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaMemcpyAsync(m + n, len, n * 8, cudaMemcpyHostToDevice, s));
-	ZG_CUDA(cudaStreamSynchronize(s));  // `rebased` is pageable
-	u8* o = c->d_out_meta.as<u8>();
-	u64* d_foff = (u64*)o;
-	u64* d_flen = d_foff + n;
-	u8* d_dig = (u8*)(d_flen + n);
-	u8* d_first = d_dig + n * 32;
-	u64 bytes = 0;
-	ZG_TRY(pack_core(c, A, c->d_blob.as<u8>(), m, m + n, n, d_dig, d_first, d_foff, d_flen, c->d_frames.as<u8>(), frames_cap, &bytes));
-	if (digests) ZG_CUDA(cudaMemcpyAsync(digests, d_dig, n * 32, cudaMemcpyDeviceToHost, s));
-	if (first) ZG_CUDA(cudaMemcpyAsync(first, d_first, n, cudaMemcpyDeviceToHost, s));
-	if (frame_off) ZG_CUDA(cudaMemcpyAsync(frame_off, d_foff, n * 8, cudaMemcpyDeviceToHost, s));
-	if (frame_len) ZG_CUDA(cudaMemcpyAsync(frame_len, d_flen, n * 8, cudaMemcpyDeviceToHost, s));
-	if (bytes) ZG_CUDA(cudaMemcpyAsync(frames_out, c->d_frames.p, bytes, cudaMemcpyDeviceToHost, s));
-	ZG_CUDA(cudaStreamSynchronize(s));
-	if (frames_bytes) *frames_bytes = bytes;
+	// slices: [first file, one past last), and the span of the host blob each one touches
+	struct Slice {
+		u64 i0, i1, lo, hi, bytes;
+	};
+	std::vector<Slice> sl;
+	{
+		Slice cur{0, 0, ~0ull, 0, 0};
+		u64 spans = 0, total = 0;
+		for (u64 i = 0; i < n; i++) {
+			cur.lo = off[i] < cur.lo ? off[i] : cur.lo;
+			cur.hi = off[i] + len[i] > cur.hi ? off[i] + len[i] : cur.hi;
+			cur.bytes += len[i];
+			if (cur.bytes >= g_zg_slice_bytes || i + 1 == n) {
+				cur.i1 = i + 1;
+				sl.push_back(cur);
+				spans += cur.hi - cur.lo;
+				total += cur.bytes;
+				cur = Slice{i + 1, 0, ~0ull, 0, 0};
+			}
+		}
+		if (sl.size() > 1 && spans > 2 * total + (64ull << 20)) {  // files scattered over the blob: slicing would re-copy it
+			Slice all{0, n, ~0ull, 0, total};
+			for (u64 i = 0; i < n; i++) {
+				all.lo = off[i] < all.lo ? off[i] : all.lo;
+				all.hi = off[i] + len[i] > all.hi ? off[i] + len[i] : all.hi;
+			}
+			sl.assign(1, all);
+		}
+	}
+	auto upload = [&](size_t k) -> size_t {
+		const Slice& q = sl[k];
+		auto& st = c->stage[k & 1];
+		u64 m = q.i1 - q.i0, span = q.hi - q.lo;
+		u64 cap = q.bytes + q.bytes / 128 + 64 * m + 4096;
+		ZG_ALLOC(st.d_blob.reserve(span + 64));
+		ZG_ALLOC(st.d_meta.reserve(m * 16));
+		ZG_ALLOC(st.d_out_meta.reserve(m * 49 + 64));
+		ZG_ALLOC(st.d_frames.reserve(cap + 64));
+		ZG_ALLOC(st.h_meta.reserve(m * 8));
+		u64* h = st.h_meta.as<u64>();
+		for (u64 i = 0; i < m; i++) h[i] = off[q.i0 + i] - q.lo;
+		ZG_CUDA(cudaStreamWaitEvent(c->s_in, st.out_done, 0));  // the stage's previous results have left
+		u64* dm = st.d_meta.as<u64>();
+		if (span) ZG_CUDA(cudaMemcpyAsync(st.d_blob.p, blob + q.lo, span, cudaMemcpyHostToDevice, c->s_in));
+		ZG_CUDA(cudaMemcpyAsync(dm, h, m * 8, cudaMemcpyHostToDevice, c->s_in));
+		ZG_CUDA(cudaMemcpyAsync(dm + m, len + q.i0, m * 8, cudaMemcpyHostToDevice, c->s_in));
+		ZG_CUDA(cudaEventRecord(st.in_done, c->s_in));
+		return 0;
+	};
+	size_t r = upload(0);
+	u64 written = 0;
+	for (size_t k = 0; k < sl.size() && !zg_is_error(r); k++) {
+		const Slice& q = sl[k];
+		auto& st = c->stage[k & 1];
+		u64 m = q.i1 - q.i0;
+		if (k + 1 < sl.size()) {
+			r = upload(k + 1);
+			if (zg_is_error(r)) break;
+		}
+		u8* o = st.d_out_meta.as<u8>();
+		u64* d_foff = (u64*)o;
+		u64* d_flen = d_foff + m;
+		u8* d_dig = (u8*)(d_flen + m);
+		u8* d_first = d_dig + m * 32;
+		u64* dm = st.d_meta.as<u64>();
+		u64 cap = zg_min<u64>(st.d_frames.cap, frames_cap - written);
+		u64 bytes = 0;
+		if (cudaStreamWaitEvent(s, st.in_done, 0) != cudaSuccess) {
+			r = ZG_ERR(ZG_error_device);
+			break;
+		}
+		r = pack_core(c, A, st.d_blob.as<u8>(), dm, dm + m, m, d_dig, d_first, d_foff, d_flen, st.d_frames.as<u8>(), cap, &bytes);
+		if (zg_is_error(r)) break;
+		// pack_core returns with the stream drained: the results can leave while the next slice computes
+		cudaError_t e = cudaSuccess;
+		if (digests) e = cudaMemcpyAsync(digests + 32 * q.i0, d_dig, m * 32, cudaMemcpyDeviceToHost, c->s_out);
+		if (first && e == cudaSuccess) e = cudaMemcpyAsync(first + q.i0, d_first, m, cudaMemcpyDeviceToHost, c->s_out);
+		if (frame_off && e == cudaSuccess) e = cudaMemcpyAsync(frame_off + q.i0, d_foff, m * 8, cudaMemcpyDeviceToHost, c->s_out);
+		if (frame_len && e == cudaSuccess) e = cudaMemcpyAsync(frame_len + q.i0, d_flen, m * 8, cudaMemcpyDeviceToHost, c->s_out);
+		if (bytes && e == cudaSuccess) e = cudaMemcpyAsync(frames_out + written, st.d_frames.p, bytes, cudaMemcpyDeviceToHost, c->s_out);
+		if (e == cudaSuccess) e = cudaEventRecord(st.out_done, c->s_out);
+		if (e != cudaSuccess) {
+			r = ZG_ERR(ZG_error_device);
+			break;
+		}
+		written += bytes;
+	}
+	cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_out);
+	if (zg_is_error(r)) return r;
+	if (e1 != cudaSuccess || e2 != cudaSuccess) return ZG_ERR(ZG_error_device);
+	if (frames_bytes) *frames_bytes = written;
 	return 0;
 }
 

@@ -52,14 +52,17 @@ k_blake3_files(const u8* __restrict__ blob, const u64* __restrict__ off, const u
 }
 
 // Small files (<= B3_SMALL_CHUNKS chunks, i.e. almost every file of a source tree): ONE LANE per
-// file.  A warp per file leaves most lanes idle when files average ten chunks; here every lane
-// streams its own file and all lanes meet in one converged b3_compress per step.  A step is either
-// the next 64-byte block of the lane's current chunk or a parent merge of its subtree stack -- the
-// same compression function with different inputs, so divergence is confined to the short
-// preparation around it.  Lanes take the next file from a queue as they finish.
+// 8-chunk unit.  A warp per file leaves most lanes idle when files average ten chunks; here every
+// lane streams its own 8 KiB unit (an aligned 8-chunk group is a complete subtree of BLAKE3's
+// left-full tree, the last partial group is the right spine) and all lanes meet in one converged
+// b3_compress per step.  A step is either the next 64-byte block of the lane's current chunk or a
+// parent merge of its subtree stack -- the same compression function with different inputs, so
+// divergence is confined to the short preparation around it.  Lanes take the next unit from a
+// queue as they finish; a file's <= 8 unit nodes are folded by k_blake3_unit_merge.
 #define B3_SMALL_CHUNKS 64u
+#define B3_UNIT_CHUNKS 8u
 #define B3_SMALL_THREADS 128
-#define B3_SMALL_DEPTH 7   // subtree stack: <= log2(64) + 1 entries
+#define B3_SMALL_DEPTH 4   // subtree stack inside a unit: <= log2(8) + 1 entries
 
 // message words of a block of `len` (1..64) bytes at an arbitrarily aligned address, zero padded;
 // only aligned words holding at least one message byte are read
@@ -78,37 +81,61 @@ ZG_DEV void b3_load_block(const u8* p, u32 len, u32 m[16]) {
 	}
 }
 
+// units per file (0 for files left to the warp-per-file kernel, which are listed in `med`)
+__global__ void __launch_bounds__(256) k_blake3_unit_count(const u64* __restrict__ len, u64 n, u64* __restrict__ ucount, u32* __restrict__ med,
+                                                            u32* __restrict__ counters) {
+	u64 f = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= n) return;
+	u64 chunks = (len[f] + 1023) >> 10;
+	if (chunks > B3_SMALL_CHUNKS) {
+		med[atomicAdd(&counters[2], 1u)] = (u32)f;
+		ucount[f] = 0;
+	} else {
+		ucount[f] = chunks == 0 ? 1 : (chunks + B3_UNIT_CHUNKS - 1) / B3_UNIT_CHUNKS;
+	}
+}
+
 __global__ void __launch_bounds__(B3_SMALL_THREADS)
 k_blake3_small(const u8* __restrict__ blob, const u64* __restrict__ off, const u64* __restrict__ len, u64 n,
-               u8* __restrict__ digests, u32* __restrict__ med, u32* __restrict__ counters) {
+               const u64* __restrict__ ubase, const u64* __restrict__ utotal, u8* __restrict__ digests, u32* __restrict__ nodes,
+               u32* __restrict__ counters) {
 	// subtree stack of every thread: [depth][word][thread] keeps the accesses conflict-free
 	__shared__ u32 stack[B3_SMALL_DEPTH][8][B3_SMALL_THREADS];
 	u32 tid = threadIdx.x;
-	const u8* p = blob;   // next block of the current file
-	u64 f = 0;
-	u32 left = 0;         // bytes of the file not yet compressed
-	u32 nchunks = 0, chunk = 0, blk = 0, depth = 0, merges = 0;
-	bool active = false, final_merge = false;
+	u64 total = *utotal;
+	const u8* p = blob;   // next block of the current unit
+	u64 f = 0, g = 0;
+	u32 left = 0;         // bytes of the unit not yet compressed
+	u32 chunk = 0, chunk_end = 0, done_in_unit = 0, blk = 0, depth = 0, merges = 0;
+	bool active = false, final_merge = false, whole = false, dry = false;
 	u32 cv[8];
 	b3_set_iv(cv);
 	for (;;) {
-		// ---- take files until this lane has one to hash (or the queue is dry) ----
-		while (!active) {
-			u64 g = atomicAdd(&counters[1], 1u);
-			if (g >= n) break;
-			u64 l = len[g];
-			if (((l + 1023) >> 10) > B3_SMALL_CHUNKS) {
-				med[atomicAdd(&counters[2], 1u)] = (u32)g;  // left to the warp-per-file kernel
-				continue;
+		// ---- take the next unit (or find the queue dry) ----
+		if (!active && !dry) {
+			g = atomicAdd(&counters[1], 1u);
+			dry = g >= total;
+			if (!dry) {
+				u64 lo = 0, hi = n - 1;  // the unit's file: last f with ubase[f] <= g
+				while (lo < hi) {
+					u64 mid = (lo + hi + 1) >> 1;
+					if (ubase[mid] <= g) lo = mid;
+					else hi = mid - 1;
+				}
+				f = lo;
+				u64 l = len[f];
+				u32 u = (u32)(g - ubase[f]);
+				u32 nchunks = l == 0 ? 1u : (u32)((l + 1023) >> 10);
+				chunk = u * B3_UNIT_CHUNKS;
+				chunk_end = zg_min<u32>(chunk + B3_UNIT_CHUNKS, nchunks);
+				whole = nchunks <= B3_UNIT_CHUNKS;
+				p = blob + off[f] + (u64)chunk * 1024;
+				left = (u32)zg_min<u64>(l - (u64)chunk * 1024, (u64)(chunk_end - chunk) * 1024);
+				done_in_unit = blk = depth = merges = 0;
+				final_merge = false;
+				active = true;
+				b3_set_iv(cv);
 			}
-			f = g;
-			p = blob + off[g];
-			left = (u32)l;
-			nchunks = l == 0 ? 1u : (u32)((l + 1023) >> 10);
-			chunk = blk = depth = merges = 0;
-			final_merge = false;
-			active = true;
-			b3_set_iv(cv);
 		}
 		if (!__any_sync(ZG_FULL, active)) break;
 		// ---- prepare this step's compression ----
@@ -122,15 +149,15 @@ k_blake3_small(const u8* __restrict__ blob, const u64* __restrict__ off, const u
 				m[8 + i] = cv[i];
 			}
 			b3_set_iv(cv);
-			flags = B3_PARENT | ((final_merge && merges == 1) ? B3_ROOT : 0u);
+			flags = B3_PARENT | ((final_merge && merges == 1 && whole) ? B3_ROOT : 0u);
 		} else if (active) {
 			u32 in_chunk = zg_min<u32>(left, 1024u - 64u * blk);  // bytes of this chunk still to go
 			blen = zg_min<u32>(in_chunk, 64u);
 			bool last_blk = in_chunk <= 64;
-			if (blen == 64) b3_load_block(p, 64, m);
-			else b3_load_block(p, blen, m);  // blen == 0 only for the empty file: all zero words, nothing read
+			b3_load_block(p, blen, m);  // blen == 0 only for the empty file: all zero words, nothing read
 			ctr = chunk;
-			flags = (blk == 0 ? B3_CHUNK_START : 0u) | (last_blk ? B3_CHUNK_END : 0u) | ((last_blk && nchunks == 1) ? B3_ROOT : 0u);
+			flags = (blk == 0 ? B3_CHUNK_START : 0u) | (last_blk ? B3_CHUNK_END : 0u) |
+			        ((last_blk && whole && chunk_end == 1) ? B3_ROOT : 0u);
 		} else {
 			ZG_UNROLL
 			for (int i = 0; i < 16; i++) m[i] = 0;
@@ -158,15 +185,16 @@ k_blake3_small(const u8* __restrict__ blob, const u64* __restrict__ off, const u
 			blk++;
 			if (last_blk) {
 				chunk++;
+				done_in_unit++;
 				blk = 0;
-				if (chunk == nchunks) {
-					// last chunk: fold the whole stack onto it, the last merge is the root
+				if (chunk == chunk_end) {
+					// last chunk of the unit: fold the whole stack onto it
 					final_merge = true;
 					merges = depth;
 					if (merges == 0) done = true;
 				} else {
-					// completed `chunk` chunks: merge while that count is even, then push
-					merges = (u32)__ffs((int)chunk) - 1u;
+					// completed `done_in_unit` chunks: merge while that count is even, then push
+					merges = (u32)__ffs((int)done_in_unit) - 1u;
 					if (merges == 0) {
 						ZG_UNROLL
 						for (int i = 0; i < 8; i++) stack[depth][i][tid] = cv[i];
@@ -177,10 +205,46 @@ k_blake3_small(const u8* __restrict__ blob, const u64* __restrict__ off, const u
 			}
 		}
 		if (done) {
-			b3_store_digest(digests + 32 * f, cv);
+			if (whole) b3_store_digest(digests + 32 * f, cv);
+			else {
+				ZG_UNROLL
+				for (int i = 0; i < 8; i++) nodes[8 * g + i] = cv[i];
+			}
 			active = false;
 		}
 	}
+}
+
+// files of 2..8 units: fold the unit nodes (left-full over units, like chunks), one lane per file
+__global__ void __launch_bounds__(256) k_blake3_unit_merge(const u64* __restrict__ ucount, const u64* __restrict__ ubase, u64 n,
+                                                            const u32* __restrict__ nodes, u8* __restrict__ digests) {
+	u64 f = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= n) return;
+	u32 U = (u32)ucount[f];
+	if (U < 2) return;
+	const u32* nd = nodes + 8 * ubase[f];
+	u32 st[3][8];  // U <= 8: at most 3 pending subtrees
+	u32 depth = 0;
+	u32 cv[8];
+	for (u32 i = 0; i < U; i++) {
+		ZG_UNROLL
+		for (int j = 0; j < 8; j++) cv[j] = nd[8 * i + j];
+		bool last = i + 1 == U;
+		u32 merges = last ? depth : (u32)__ffs((int)(i + 1)) - 1u;
+		for (u32 k = 0; k < merges; k++) {
+			u32 o[8];
+			depth--;
+			b3_parent_cv(st[depth], cv, last && k + 1 == merges, o);
+			ZG_UNROLL
+			for (int j = 0; j < 8; j++) cv[j] = o[j];
+		}
+		if (!last) {
+			ZG_UNROLL
+			for (int j = 0; j < 8; j++) st[depth][j] = cv[j];
+			depth++;
+		}
+	}
+	b3_store_digest(digests + 32 * f, cv);
 }
 
 // big files, pass 1: group g of 32 chunks -> nodes[g]
@@ -252,6 +316,10 @@ k_blake3_big_finish(const u64* __restrict__ big, const u64* __restrict__ base, u
 void zg_b3work_free(ZgB3Work& w) {
 	w.big.release();
 	w.med.release();
+	w.ucount.release();
+	w.ubase.release();
+	w.unodes.release();
+	w.tiles.release();
 	w.ctr.release();
 	w.base.release();
 	w.nodes.release();
@@ -264,11 +332,19 @@ size_t zg_blake3_run(cudaStream_t s, ZgB3Work& w, const u8* blob, const u64* off
 	if (w.big.reserve(n * 16) || w.med.reserve(n * 4) || w.ctr.reserve(16) || w.h.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.ctr.p, 0, 16, s);  // [0] big files, [1] small-kernel queue, [2] medium files
 	u32* hcount = w.h.as<u32>();
+	if (w.ucount.reserve(n * 8) || w.ubase.reserve(n * 8 + 8)) return ZG_ERR(ZG_error_memory_allocation);
+	// every file contributes <= 8 units; the node array is sized for the worst case
+	if (w.unodes.reserve(n * 8 * 32)) return ZG_ERR(ZG_error_memory_allocation);
 	zg_prof_begin(ZG_K_BLAKE3, s);
+	ZG_LAUNCH(k_blake3_unit_count, (u32)((n + 255) / 256), 256, 0, s, len, n, w.ucount.as<u64>(), w.med.as<u32>(), w.ctr.as<u32>());
+	size_t sr = zg_scan_run(s, w.tiles, w.ucount.as<u64>(), n, 0, w.ubase.as<u64>(), w.ubase.as<u64>() + n);
+	if (zg_is_error(sr)) return sr;
 	u32 grid = (u32)zg_min<u64>((n + B3_SMALL_THREADS - 1) / B3_SMALL_THREADS, (u64)zg_sm_count() * 7);
-	ZG_LAUNCH(k_blake3_small, grid, B3_SMALL_THREADS, 0, s, blob, off, len, n, digests, w.med.as<u32>(), w.ctr.as<u32>());
+	ZG_LAUNCH(k_blake3_small, grid, B3_SMALL_THREADS, 0, s, blob, off, len, n, w.ubase.as<u64>(), w.ubase.as<u64>() + n, digests,
+	          w.unodes.as<u32>(), w.ctr.as<u32>());
+	ZG_LAUNCH(k_blake3_unit_merge, (u32)((n + 255) / 256), 256, 0, s, w.ucount.as<u64>(), w.ubase.as<u64>(), n, w.unodes.as<u32>(), digests);
 	zg_prof_end(ZG_K_BLAKE3, s);
-	ZG_COUNT_LAUNCH();
+	g_zg_launches += 3;
 	cudaMemcpyAsync(hcount, w.ctr.p, 12, cudaMemcpyDeviceToHost, s);
 	if (cudaStreamSynchronize(s) != cudaSuccess) return ZG_ERR(ZG_error_device);
 	u32 nmed = hcount[2];

@@ -5,6 +5,7 @@
 
 #define ZG_ERR(code) ((size_t)0 - (size_t)(code))
 
+extern uint64_t g_zg_slice_bytes;  // host-buffer API: input bytes per pipelined slice (tests shrink it)
 extern uint64_t g_zg_launches;  // kernels launched by this library (bench.py's gpu_launches)
 #define ZG_COUNT_LAUNCH() (++g_zg_launches)
 
@@ -58,6 +59,7 @@ int zg_sm_count();
 struct ZgB3Work {
 	ZgBuf big;     // u64 pairs {file idx, len}
 	ZgBuf med;     // u32 indices of files above 64 chunks
+	ZgBuf ucount, ubase, unodes, tiles;  // 8-chunk units of the small files: count / prefix per file, unit nodes, scan scratch
 	ZgBuf ctr;     // u32 counters
 	ZgBuf base;    // u64 group prefix per big file
 	ZgBuf nodes;   // level-5 chaining values of big files
@@ -109,6 +111,9 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
                           int level);
 
 // ---- per-kernel device timing (abi.cu): CUDA events on the launching stream, off by default ----
-enum { ZG_K_BLAKE3 = 0, ZG_K_ENCODE = 1, ZG_K_DECODE = 2, ZG_K_ASSEMBLE = 3, ZG_K_XXH64 = 4, ZG_K_DEDUP = 5, ZG_K_COUNT = 6 };
+enum {
+	ZG_K_BLAKE3 = 0, ZG_K_ENCODE = 1 /* the whole encode pass */, ZG_K_DECODE = 2, ZG_K_ASSEMBLE = 3, ZG_K_XXH64 = 4, ZG_K_DEDUP = 5,
+	ZG_K_MATCH = 6, ZG_K_LITERALS = 7, ZG_K_SEQUENCES = 8, ZG_K_COUNT = 9
+};
 void zg_prof_begin(int k, cudaStream_t s);
 void zg_prof_end(int k, cudaStream_t s);

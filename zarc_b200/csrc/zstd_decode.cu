@@ -32,6 +32,7 @@
 #define ZD_TAB_SLOT 1280u                // u32 entries per lane: LL 512 | ML 512 | OF 256
 #define ZD_HUFSAVE 272u                  // bytes per lane: 256 weights + count
 #define ZD_OFF_MAX ((1u << 28) - 1u)
+#define ZD_BATCH_BYTES (64u << 10)        // least compressed bytes per warp batch (see the hand-out in the kernel)
 
 struct ZdWarp {
 	u32 tab[512];      // table under construction (FSE sequence table or Huffman-weight table)
@@ -883,11 +884,35 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 	u32* my_slot = tabs + (gw * 32 + lane) * ZD_TAB_SLOT;
 	u8* hufsave0 = hufsaves + gw * 32 * ZD_HUFSAVE;
 	for (;;) {
-		u32 base = 0;
-		if (lane == 0) base = atomicAdd(queue, 32u);
+		// Hand-out: frames come largest first.  A batch is up to 32 frames, but (a) no more than about
+		// ZD_BATCH_BYTES of compressed input -- the phases around the lane-parallel sequence decode run
+		// frame after frame, so 32 of the largest frames in one warp would be the kernel's tail --
+		// and (b) smaller towards the end, so that the last round is spread over all warps.
+		u32 base = 0, want = 32;
+		if (lane == 0) {
+			for (;;) {
+				u32 taken = *(volatile u32*)queue;
+				if (taken >= nframes) {
+					base = taken;
+					break;
+				}
+				u64 left = nframes - taken;
+				u64 share = left / (2ull * gridDim.x * ZD_WARPS);
+				u64 flen = len[perm ? perm[taken] : taken];
+				// a quarter of a warp's fair share of the input, but at least ZD_BATCH_BYTES
+				u64 cap = zg_max<u64>(ZD_BATCH_BYTES, archive_len / (4ull * gridDim.x * ZD_WARPS));
+				u64 fit = cap / (flen ? flen : 1);
+				want = (u32)zg_min<u64>(zg_min<u64>(32, zg_max<u64>(4, share)), zg_max<u64>(2, fit));
+				if (atomicCAS(queue, taken, taken + want) == taken) {
+					base = taken;
+					break;
+				}
+			}
+		}
 		base = __shfl_sync(ZG_FULL, base, 0);
+		want = __shfl_sync(ZG_FULL, want, 0);
 		if (base >= nframes) break;
-		bool mine = (u64)base + lane < nframes;
+		bool mine = lane < want && (u64)base + lane < nframes;
 		u64 k = mine ? (perm ? (u64)perm[base + lane] : (u64)base + lane) : 0;
 		// ---- lane-private frame header ----
 		ZdLane L;

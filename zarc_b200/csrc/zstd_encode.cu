@@ -1496,9 +1496,15 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	u32* q = w.queue.as<u32>();
 	for (u32 k = 0; k < nchunks; k++) {
 		u32* qk = q + (size_t)k * ZE_NQ;
+		zg_prof_begin(ZG_K_MATCH, s);
 		ZG_LAUNCH(k_zstd_match_blocks, grid_m, ZE_WARPS * 32, smem_m, s, J, k, qk + 0, prm);
+		zg_prof_end(ZG_K_MATCH, s);
+		zg_prof_begin(ZG_K_LITERALS, s);
 		ZG_LAUNCH(k_zstd_literals, grid_e, ZE_WARPS * 32, smem_l, s, J, k, qk + 1);
+		zg_prof_end(ZG_K_LITERALS, s);
+		zg_prof_begin(ZG_K_SEQUENCES, s);
 		ZG_LAUNCH(k_zstd_sequences, grid_e, ZE_WARPS * 32, smem_q, s, J, k, qk + 2);
+		zg_prof_end(ZG_K_SEQUENCES, s);
 		g_zg_launches += 3;
 	}
 	zg_prof_end(ZG_K_ENCODE, s);
