@@ -92,9 +92,27 @@ def build_emu(force: bool = False) -> str:
     return EMU_SO
 
 
+HOST_DIR = os.path.join(ROOT, "zarc_b200", "host")
+HOST_BIN = os.path.join(ROOT, "zarc_b200", "zarc-b200")
+
+
+def build_host(force: bool = False) -> str:
+    """g++ -> zarc_b200/zarc-b200: the C++ host (Encoder/Decoder mirror, container format, CLI).  It binds
+    libzarcgpu.so at run time (dlopen); no codec is linked into it."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("zarc_host.cpp", "zarc_cli.cpp")]
+    deps = glob.glob(os.path.join(HOST_DIR, "*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(os.path.getmtime(f) for f in deps):
+        return HOST_BIN
+    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Wno-missing-field-initializers",
+                           *srcs, "-o", HOST_BIN, "-ldl"])
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["product"]
     if "product" in which:
         print(build_product(force="--force" in which, verbose="-v" in which))
     if "emu" in which:
         print(build_emu(force="--force" in which))
+    if "host" in which:
+        print(build_host(force="--force" in which))
