@@ -6,6 +6,7 @@
 #include <cstring>
 #include <fcntl.h>
 #include <filesystem>
+#include <memory>
 #include <regex>
 #include <string>
 #include <sys/stat.h>
@@ -18,6 +19,23 @@
 
 namespace fs = std::filesystem;
 using namespace zarc;
+
+// $ZARC_TIMING=1: wall-clock of the phases on stderr
+static double now_s() {
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+// page-locking a buffer costs about as much as copying it a few times: only worth it for multi-pass jobs
+static const uint64_t PIN_THRESHOLD = 1ull << 30;
+static const bool TIMING = getenv("ZARC_TIMING") != nullptr;
+static double t_last = now_s();
+static void lap(const char* what) {
+	if (!TIMING) return;
+	double t = now_s();
+	fprintf(stderr, "[timing] %-28s %8.1f ms\n", what, (t - t_last) * 1e3);
+	t_last = t;
+}
 
 // content bytes gathered before one GPU pass ($ZARC_BATCH_MB overrides; tests use it to force several passes)
 static const uint64_t BATCH_BYTES = getenv("ZARC_BATCH_MB") ? (uint64_t)atoll(getenv("ZARC_BATCH_MB")) << 20 : 1ull << 30;
@@ -90,20 +108,69 @@ static int cmd_pack(int argc, char** argv) {
 	if (output.empty() || paths.empty()) usage(2);
 	std::FILE* out = fopen(output.c_str(), "wb");
 	if (!out) { fprintf(stderr, "error: %s: %s\n", output.c_str(), strerror(errno)); return 1; }
+	lap("start");
 	Encoder zarc(out);
+	lap("encoder (context) create");
 	zarc.set_zstd_parameter(ZstdParameter::ChecksumFlag, 1);  // pack.rs:227-228
 	if (have_level) zarc.set_zstd_parameter(ZstdParameter::CompressionLevel, level);
 	for (auto& pv : params) zarc.set_zstd_parameter(pv.first, pv.second);
 
 	GpuLib& g = gpu();
-	uint8_t* blob = (uint8_t*)g.zg_alloc_pinned(BATCH_BYTES + 1);
-	if (!blob) { fprintf(stderr, "error: cannot allocate the pinned batch buffer\n"); return 1; }
+	// the walk (WalkDir order: a root first, then its contents in directory order, pack.rs:246)
+	struct Walked {
+		std::string path;
+		bool regular;
+		uint64_t size;
+	};
+	std::vector<Walked> walked;
+	uint64_t total_content = 0;
+	auto note = [&](const std::string& path, const fs::file_status& st) {
+		bool reg = fs::is_regular_file(st);
+		uint64_t sz = 0;
+		if (reg) {
+			std::error_code ec2;
+			sz = (uint64_t)fs::file_size(path, ec2);
+			if (ec2) sz = 0;
+		}
+		walked.push_back({path, reg, sz});
+		total_content += sz;
+	};
+	for (const std::string& root : paths) {
+		std::error_code ec;
+		fs::file_status rs = follow ? fs::status(root, ec) : fs::symlink_status(root, ec);
+		if (ec) { fprintf(stderr, "read error: %s: %s\n", root.c_str(), ec.message().c_str()); continue; }
+		note(root, rs);
+		if (!fs::is_directory(rs)) continue;
+		auto opts = follow ? fs::directory_options::follow_directory_symlink : fs::directory_options::none;
+		for (auto it = fs::recursive_directory_iterator(root, opts | fs::directory_options::skip_permission_denied, ec);
+		     it != fs::recursive_directory_iterator(); it.increment(ec)) {
+			if (ec) { fprintf(stderr, "read error: %s\n", ec.message().c_str()); break; }
+			fs::file_status st = follow ? it->status(ec) : it->symlink_status(ec);
+			if (ec) { fprintf(stderr, "read error: %s: %s\n", it->path().c_str(), ec.message().c_str()); continue; }
+			note(it->path().string(), st);
+		}
+	}
+	lap("walk");
+	// the batch buffer: page-locked when the job is large enough for the locking to pay for itself
+	uint64_t batch_cap = std::min<uint64_t>(BATCH_BYTES, total_content + (1 << 16));
+	bool pinned = total_content > PIN_THRESHOLD;
+	std::unique_ptr<uint8_t[]> pageable;
+	uint8_t* blob = nullptr;
+	if (pinned) blob = (uint8_t*)g.zg_alloc_pinned(batch_cap + 1);
+	else {
+		pageable.reset(new uint8_t[batch_cap + 1]);  // not zero-filled
+		blob = pageable.get();
+	}
+	if (!blob) { fprintf(stderr, "error: cannot allocate the batch buffer\n"); return 1; }
+	lap("batch buffer");
 	std::vector<uint8_t> big;  // a single file larger than a batch goes on its own
 	std::vector<uint64_t> offs, lens;
 	std::vector<PendingEntry> pending;
 	uint64_t used = 0;
 	auto flush = [&]() {
+		lap("walk + read files");
 		std::vector<Digest> digests = zarc.add_data_frames(blob, offs.data(), lens.data(), offs.size());
+		lap("add_data_frames (GPU + write)");
 		for (auto& pe : pending) {
 			if (pe.has_content) pe.file.digest = digests[pe.content_index];
 			zarc.add_file_entry(std::move(pe.file));
@@ -122,7 +189,7 @@ static int cmd_pack(int argc, char** argv) {
 			struct stat st;
 			fstat(fd, &st);
 			uint64_t n = (uint64_t)st.st_size;
-			if (n > BATCH_BYTES) {  // oversized: flush what is pending, then this file alone from pageable memory
+			if (n > batch_cap) {  // oversized: flush what is pending, then this file alone from pageable memory
 				flush();
 				big.resize(n);
 				uint64_t done = 0;
@@ -138,7 +205,7 @@ static int cmd_pack(int argc, char** argv) {
 				zarc.add_file_entry(std::move(pe.file));
 				return;
 			}
-			if (used + n > BATCH_BYTES) flush();
+			if (used + n > batch_cap) flush();
 			uint64_t done = 0;
 			while (done < n) {
 				ssize_t k = read(fd, blob + used + done, n - done);
@@ -155,29 +222,15 @@ static int cmd_pack(int argc, char** argv) {
 		pending.push_back(std::move(pe));
 	};
 	try {
-		for (const std::string& root : paths) {
-			// WalkDir yields the root first, then its contents in directory order (pack.rs:246)
-			std::error_code ec;
-			fs::file_status rs = follow ? fs::status(root, ec) : fs::symlink_status(root, ec);
-			if (ec) { fprintf(stderr, "read error: %s: %s\n", root.c_str(), ec.message().c_str()); continue; }
-			visit(root, fs::is_regular_file(rs));
-			if (!fs::is_directory(rs)) continue;
-			auto opts = follow ? fs::directory_options::follow_directory_symlink : fs::directory_options::none;
-			for (auto it = fs::recursive_directory_iterator(root, opts | fs::directory_options::skip_permission_denied, ec);
-			     it != fs::recursive_directory_iterator(); it.increment(ec)) {
-				if (ec) { fprintf(stderr, "read error: %s\n", ec.message().c_str()); break; }
-				fs::file_status s = follow ? it->status(ec) : it->symlink_status(ec);
-				if (ec) { fprintf(stderr, "read error: %s: %s\n", it->path().c_str(), ec.message().c_str()); continue; }
-				visit(it->path().string(), fs::is_regular_file(s));
-			}
-		}
+		for (const Walked& w : walked) visit(w.path, w.regular);
 		flush();
 		Digest digest = zarc.finalise();
-		g.zg_free_pinned(blob);
+		lap("finalise");
+		if (pinned) g.zg_free_pinned(blob);
 		fclose(out);
 		printf("digest: %s\n", digest.base64().c_str());
 	} catch (const std::exception& e) {
-		g.zg_free_pinned(blob);
+		if (pinned) g.zg_free_pinned(blob);
 		fclose(out);
 		fprintf(stderr, "error: %s\n", e.what());
 		return 1;
@@ -223,7 +276,9 @@ static int cmd_unpack(int argc, char** argv) {
 	}
 	if (input.empty()) usage(2);
 	try {
+		lap("start");
 		Decoder zarc = Decoder::open(input);
+		lap("decoder (context) create");
 		if (!verify.empty()) {
 			if (Digest::from_base64(verify) != zarc.trailer().digest) {
 				fprintf(stderr, "integrity failure: zarc file digest is %s\n", zarc.trailer().digest.base64().c_str());
@@ -276,6 +331,7 @@ static int cmd_unpack(int argc, char** argv) {
 			}
 		}
 		flush();
+		lap("read_content_frames (GPU) + write files");
 		fprintf(stderr, "unpacked %llu files\n", (unsigned long long)unpacked);
 	} catch (const std::exception& e) {
 		fprintf(stderr, "error: %s\n", e.what());

@@ -599,6 +599,29 @@ void Trailer::make_offset_positive(uint64_t file_length) {
 }
 
 // ================================================================================================
+// staging buffer for the host-buffer ABI: page-locked when large (the copies then overlap the kernels),
+// plain memory when small (locking pages costs more than it saves on a one-pass job)
+struct HostBuffer {
+	uint8_t* p = nullptr;
+	bool pinned = false;
+	std::unique_ptr<uint8_t[]> plain;
+	explicit HostBuffer(uint64_t n) {
+		if (n > (1ull << 30)) {
+			p = (uint8_t*)gpu().zg_alloc_pinned(n + 1);
+			pinned = p != nullptr;
+		}
+		if (!p) {
+			plain.reset(new uint8_t[n + 1]);  // not zero-filled
+			p = plain.get();
+		}
+	}
+	~HostBuffer() {
+		if (pinned) gpu().zg_free_pinned(p);
+	}
+	HostBuffer(const HostBuffer&) = delete;
+};
+
+// ================================================================================================
 // Encoder
 Encoder::Encoder(std::FILE* writer) : writer_(writer) {
 	GpuLib& g = gpu();
@@ -632,21 +655,11 @@ std::vector<Digest> Encoder::add_data_frames(const uint8_t* blob, const uint64_t
 	for (size_t i = 0; i < n; i++) cap += len[i] + std::max<uint64_t>(1024, len[i] / 10);  // lowlevel_frames.rs:21
 	std::vector<uint8_t> digests(n * DIGEST_LEN), first(n);
 	std::vector<uint64_t> foff(n), flen(n);
-	uint8_t* frames = (uint8_t*)g.zg_alloc_pinned(cap);
-	if (!frames) throw Error("failed allocating the frame buffer");
+	HostBuffer fb(cap);
+	uint8_t* frames = fb.p;
 	uint64_t bytes = 0;
-	size_t r = g.zg_pack_batch((zg_cctx*)cctx_, blob, off, len, n, digests.data(), first.data(), foff.data(), flen.data(), frames, cap, &bytes);
-	if (g.zg_is_error(r)) {
-		g.zg_free_pinned(frames);
-		g.check(r, "compress");
-	}
-	try {
-		write_all(frames, bytes);
-	} catch (...) {
-		g.zg_free_pinned(frames);
-		throw;
-	}
-	g.zg_free_pinned(frames);
+	g.check(g.zg_pack_batch((zg_cctx*)cctx_, blob, off, len, n, digests.data(), first.data(), foff.data(), flen.data(), frames, cap, &bytes), "compress");
+	write_all(frames, bytes);
 	offset_ += bytes;
 	for (size_t i = 0; i < n; i++) {
 		out[i].bytes.assign(digests.begin() + i * DIGEST_LEN, digests.begin() + (i + 1) * DIGEST_LEN);
@@ -942,57 +955,38 @@ std::vector<ContentFrame> Decoder::read_content_frames(const std::vector<Digest>
 		ubytes += f->uncompressed;
 		memcpy(want.data() + i * DIGEST_LEN, f->digest.bytes.data(), DIGEST_LEN);
 	}
-	uint8_t* arch = (uint8_t*)g.zg_alloc_pinned(cbytes + 1);
-	uint8_t* plain = (uint8_t*)g.zg_alloc_pinned(ubytes + 1);
-	if (!arch || !plain) {
-		g.zg_free_pinned(arch);
-		g.zg_free_pinned(plain);
-		throw Error("failed allocating the staging buffers");
-	}
-	size_t r = 0;
+	HostBuffer abuf(cbytes), pbuf(ubytes);
+	uint8_t* arch = abuf.p;
+	uint8_t* plain = pbuf.p;
 	std::string err;
-	try {
-		int fd = ::open(path_.c_str(), O_RDONLY);
-		if (fd < 0) throw Error(path_ + ": " + strerror(errno));
-		for (size_t i = 0; i < n; i++) {
-			const Frame* f = frame(digests[i]);
-			uint64_t done = 0;
-			while (done < f->length) {
-				ssize_t k = pread(fd, arch + off[i] + done, f->length - done, (off_t)(f->offset + done));
-				if (k <= 0) {
-					close(fd);
-					throw Error(path_ + ": short read");
-				}
-				done += (uint64_t)k;
+	int fd = ::open(path_.c_str(), O_RDONLY);
+	if (fd < 0) throw Error(path_ + ": " + strerror(errno));
+	for (size_t i = 0; i < n; i++) {
+		const Frame* f = frame(digests[i]);
+		uint64_t done = 0;
+		while (done < f->length) {
+			ssize_t k = pread(fd, arch + off[i] + done, f->length - done, (off_t)(f->offset + done));
+			if (k <= 0) {
+				close(fd);
+				throw Error(path_ + ": short read");
 			}
+			done += (uint64_t)k;
 		}
-		close(fd);
-		r = g.zg_unpack_batch((zg_dctx*)dctx_, arch, cbytes, n, off.data(), len.data(), ulen.data(), want.data(), plain, ubytes, nullptr, ok.data(),
-		                      status.data());
-		if (g.zg_is_error(r)) {
-			auto code = g.zg_get_error_code(r);
-			if (code == ZG_error_device || code == ZG_error_memory_allocation || code == ZG_error_no_device) err = g.zg_error_name(r);
-		}
-		if (err.empty()) {
-			uint64_t pos = 0;
-			for (size_t i = 0; i < n; i++) {
-				if (status[i]) {
-					err = std::string("zstd: ") + g.zg_error_name((size_t)0 - status[i]);  // decode/error.rs:35-38
-					break;
-				}
-				out[i].data.assign(plain + pos, plain + pos + ulen[i]);
-				pos += ulen[i];
-				out[i].verified = ok[i] != 0;
-			}
-		}
-	} catch (...) {
-		g.zg_free_pinned(arch);
-		g.zg_free_pinned(plain);
-		throw;
 	}
-	g.zg_free_pinned(arch);
-	g.zg_free_pinned(plain);
-	if (!err.empty()) throw Error(err);
+	close(fd);
+	size_t r = g.zg_unpack_batch((zg_dctx*)dctx_, arch, cbytes, n, off.data(), len.data(), ulen.data(), want.data(), plain, ubytes, nullptr, ok.data(),
+	                             status.data());
+	if (g.zg_is_error(r)) {
+		auto code = g.zg_get_error_code(r);
+		if (code == ZG_error_device || code == ZG_error_memory_allocation || code == ZG_error_no_device) throw Error(g.zg_error_name(r));
+	}
+	uint64_t pos = 0;
+	for (size_t i = 0; i < n; i++) {
+		if (status[i]) throw Error(std::string("zstd: ") + g.zg_error_name((size_t)0 - status[i]));  // decode/error.rs:35-38
+		out[i].data.assign(plain + pos, plain + pos + ulen[i]);
+		pos += ulen[i];
+		out[i].verified = ok[i] != 0;
+	}
 	// the digest of the decoded bytes (FrameIterator::digest): equal to the directory's when verified
 	for (size_t i = 0; i < n; i++) {
 		if (*out[i].verified) out[i].digest = digests[i];
