@@ -221,6 +221,8 @@ def main():
     assert lib.zg_device_count() > 0, "no CUDA device"
     lib.check(lib.zg_set_device(local_rank))
     if world > 1:
+        # NCCL writes its version / debug lines to stdout; rank 0's stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/zarc_bench_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream().cuda_stream

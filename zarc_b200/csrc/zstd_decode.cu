@@ -26,7 +26,9 @@
 #include "zstd_common.cuh"
 
 #define ZD_WARPS 4
+#ifndef ZD_MIN_CTAS
 #define ZD_MIN_CTAS 5                    // occupancy target: 20 warps / SM
+#endif
 #define ZD_SEQ_ARENA (1u << 17)          // u64 entries of sequence staging per warp (1 MiB)
 #define ZD_LITBUF (ZS_BLOCK_MAX + 64)    // bytes of literal staging per warp
 #define ZD_TAB_SLOT 1280u                // u32 entries per lane: LL 512 | ML 512 | OF 256

@@ -741,6 +741,19 @@ ZG_DEV void ze_ld128(const u8* p, const u8* lim, u32 out[4]) {
 	ZG_UNROLL
 	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
 }
+// the same plus the four bytes before p (0 when p is within 4 bytes of the block start `lo`)
+ZG_DEV u32 ze_ld128_prev(const u8* p, const u8* lo, const u8* lim, u32 out[4]) {
+	uintptr_t a = (uintptr_t)p;
+	const u32* w = (const u32*)(a & ~(uintptr_t)3);
+	u32 sh = (u32)(a & 3) * 8;
+	u32 x[5];
+	ZG_UNROLL
+	for (int k = 0; k < 5; k++) x[k] = (const u8*)(w + k) < lim ? w[k] : 0u;
+	u32 xm = p >= lo + 4 ? w[-1] : 0u;
+	ZG_UNROLL
+	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
+	return __funnelshift_r(xm, x[0], sh);
+}
 // number of leading equal bytes (0..16) of two 16-byte groups
 ZG_DEV u32 ze_eq16(const u32 a[4], const u32 b[4]) {
 	u32 x0 = a[0] ^ b[0], x1 = a[1] ^ b[1], x2 = a[2] ^ b[2], x3 = a[3] ^ b[3];
@@ -771,7 +784,7 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 		bool valid = pos + 4 <= n;
 		zg_prefetch_l2(src + zg_min<u32>(ip + 2048u, n - 1u));
 		u32 own[4];
-		ze_ld128(src + pos, lim, own);
+		u32 own_before = ze_ld128_prev(src + pos, src, lim, own);  // + the four bytes before this position
 		u32 v = own[0];
 		u32 h = valid ? ze_hash4(v, hlog) : (0x80000000u | lane);
 		u32 te = valid ? htab[h] : 0;
@@ -791,10 +804,10 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 			}
 		}
 		// verify + extend, 16 bytes per memory round trip (both sides loaded before any compare)
-		u32 mlen = 0;
+		u32 mlen = 0, bmatch = 0;
 		if (cand >= 0) {
 			u32 c[4];
-			ze_ld128(src + cand, lim, c);
+			u32 cand_before = ze_ld128_prev(src + cand, src, lim, c);
 			if (c[0] == v) {
 				u32 maxl = zg_min<u32>(n - pos, ZE_LANE_CAP);
 				mlen = ze_eq16(own, c);
@@ -807,6 +820,8 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 					if (e < 16) break;
 				}
 				mlen = zg_min<u32>(mlen, maxl);
+				// equal bytes right before the match, counted down from position pos - 1 (for the catch-up below)
+				if (cand >= 4) bmatch = (u32)__clz((int)(own_before ^ cand_before)) >> 3;
 			}
 		}
 		u32 moff = mlen ? pos - (u32)cand : 0;
@@ -862,8 +877,15 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 		u32 pend = __shfl_sync(ZG_FULL, my_end, below ? (int)(31u - (u32)__clz((int)below)) : 0);
 		u32 prev_end = below ? pend : mend;  // end of the nearest match that starts before this position
 		bool selme = (sel >> lane) & 1u;
-		if (selme) seq[nseq + (u32)__popc(below)] = ZE_SEQ_PACK(moff, pos - prev_end, mlen);
-		bool is_lit = inb && !selme && pos >= prev_end;
+		// a selected match also takes the pending literals right before it that equal the bytes before
+		// its source (libzstd's "catch up"), at most 4 and never across the window start: a literal
+		// that becomes match length costs no Huffman code
+		u32 bext = selme ? zg_min<u32>(bmatch, zg_min<u32>(pos - prev_end, lane)) : 0u;
+		u32 my_start = pos - bext;
+		u32 above = sel & ~(ltmask | (1u << lane));
+		u32 nstart = __shfl_sync(ZG_FULL, my_start, above ? (int)((u32)__ffs((int)above) - 1u) : 0);
+		if (selme) seq[nseq + (u32)__popc(below)] = ZE_SEQ_PACK(moff, my_start - prev_end, mlen + bext);
+		bool is_lit = inb && !selme && pos >= prev_end && !(above && pos >= nstart);
 		u32 lm = __ballot_sync(ZG_FULL, is_lit);
 		if (is_lit) lit[lpos + (u32)__popc(lm & ltmask)] = (u8)v;
 		lpos += (u32)__popc(lm);
