@@ -2,8 +2,7 @@
 //
 // The host side never links a codec: every content byte goes through the C ABI of the CUDA library.
 // The library is found through $ZARCGPU_LIB, else next to the executable, else by the loader's search
-// path.  (The CPU test-suite points $ZARCGPU_LIB at the SIMT-emulator build of the same kernel
-// sources, tests/simt_emu -- test infrastructure, never shipped.)
+// path.
 #pragma once
 #include <dlfcn.h>
 #include <stdexcept>
