@@ -48,6 +48,39 @@ def test_levels_and_features(emu, level):
     assert outs == datas and ok == [1] * len(frames)
 
 
+def periodic_cases():
+    """Matches that overlap their own output (offset < length) for every short period, matches whose source was
+    written by earlier sequences of the same 32-sequence row, and literal runs / matches around the per-lane /
+    whole-warp copy threshold."""
+    rng = np.random.default_rng(77)
+    datas = []
+    for period in list(range(1, 41)) + [63, 64, 65, 127, 200]:
+        pat = rng.integers(0, 256, period, dtype=np.uint8).tobytes()
+        reps = int(rng.integers(2, 40))
+        tail = int(rng.integers(0, period + 1))
+        datas.append(rand(int(rng.integers(0, 70)), period) + pat * reps + pat[:tail] + rand(int(rng.integers(1, 90)), period + 1))
+    # chains: each short phrase is re-used right after it was produced (dependent matches inside one row)
+    chain = bytearray(rand(24, 5))
+    for k in range(600):
+        n = int(rng.integers(4, 70))
+        back = int(rng.integers(n, min(len(chain), 300) + 1)) if len(chain) >= n else len(chain)
+        chain += chain[len(chain) - back : len(chain) - back + n]
+        if k % 3 == 0:
+            chain += rand(int(rng.integers(1, 80)), k)
+    datas.append(bytes(chain))
+    datas.append(b"".join(rand(int(rng.integers(40, 80)), k) + b"ab" * int(rng.integers(20, 45)) for k in range(200)))
+    return datas
+
+
+@pytest.mark.parametrize("level", [1, 3, 19])
+def test_periodic_and_chained_matches(emu, level):
+    datas = periodic_cases()
+    frames = [ref_path.ref_compress(d, level=level) for d in datas]
+    outs, ok, status, rc = unpack_batch(emu, frames, [len(d) for d in datas], [_b3(d) for d in datas])
+    assert rc == 0 and status == [0] * len(frames)
+    assert outs == datas and ok == [1] * len(frames)
+
+
 def test_no_checksum_frames_and_digest_mismatch(emu):
     datas = [text(5000, 1), rand(300, 2)]
     frames = [ref_path.ref_compress(d, checksum=False) for d in datas]

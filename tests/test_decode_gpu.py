@@ -15,6 +15,11 @@ def test_levels_and_features(gpu, level):
     cases.test_levels_and_features(gpu, level)
 
 
+@pytest.mark.parametrize("level", [1, 3, 19])
+def test_periodic_and_chained_matches(gpu, level):
+    cases.test_periodic_and_chained_matches(gpu, level)
+
+
 def test_no_checksum_frames_and_digest_mismatch(gpu):
     cases.test_no_checksum_frames_and_digest_mismatch(gpu)
 

@@ -57,6 +57,27 @@ def main():
     off, ln = dev(c.off), dev(c.len)
     n = c.n_files
     s = torch.cuda.current_stream().cuda_stream
+    if "pcie" in args.what:
+        # host link: pinned copies, each direction alone and both at once (what bounds the e2e number)
+        nb = 1 << 30
+        hb, hb2 = torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        db, db2 = torch.empty(nb, dtype=torch.uint8, device="cuda"), torch.empty(nb, dtype=torch.uint8, device="cuda")
+        s2 = torch.cuda.Stream()
+        best, _ = timeit(lambda: db.copy_(hb, non_blocking=True), iters=5, warmup=2)
+        res["pcie_h2d_gbs"] = nb / best / 1e6
+        best, _ = timeit(lambda: hb.copy_(db, non_blocking=True), iters=5, warmup=2)
+        res["pcie_d2h_gbs"] = nb / best / 1e6
+
+        def both():
+            s2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s2):
+                hb2.copy_(db2, non_blocking=True)
+            db.copy_(hb, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s2)
+
+        best, _ = timeit(both, iters=5, warmup=2)
+        res["pcie_duplex_gbs_each"] = nb / best / 1e6
+        del hb, hb2, db, db2
     if "blake3" in args.what:
         dig = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
         best, med = timeit(lambda: lib.check(lib.zg_blake3_batch_dev(s, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, dig.data_ptr())))

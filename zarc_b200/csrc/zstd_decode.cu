@@ -738,10 +738,52 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 	return true;
 }
 
+// Per-lane copy of n bytes between regions that do not overlap: 16 bytes per memory round trip (the
+// loads of a group are all in flight before the first store).  Only aligned words that hold at least
+// one source byte are touched.
+ZG_DEV void zd_lane_copy(u8* dst, const u8* src, u32 n) {
+	const u8* lim = src + n;
+	for (u32 k0 = 0; k0 < n; k0 += 16) {
+		uintptr_t a = (uintptr_t)(src + k0);
+		const u32* w = (const u32*)(a & ~(uintptr_t)3);
+		u32 sh = (u32)(a & 3) * 8;
+		u32 x[5];
+		ZG_UNROLL
+		for (int k = 0; k < 5; k++) x[k] = (const u8*)(w + k) < lim ? w[k] : 0u;
+		u32 m = n - k0;
+		u8* q = dst + k0;
+		ZG_UNROLL
+		for (int j = 0; j < 4; j++) {
+			if (4u * j < m) {
+				u32 v = __funnelshift_r(x[j], x[j + 1], sh);
+				q[4 * j] = (u8)v;
+				if (4u * j + 1 < m) q[4 * j + 1] = (u8)(v >> 8);
+				if (4u * j + 2 < m) q[4 * j + 2] = (u8)(v >> 16);
+				if (4u * j + 3 < m) q[4 * j + 3] = (u8)(v >> 24);
+			}
+		}
+	}
+}
+// Per-lane match copy d[i] = d[i - off] for off < ml (the match overlaps its own output): the valid
+// span [d - off, d + done) is periodic in `off`, so it is extended by non-overlapping copies whose
+// length doubles.
+ZG_DEV void zd_lane_overlap(u8* d, u32 off, u32 ml) {
+	u32 done = 0;
+	while (done < ml) {
+		u32 c = zg_min<u32>(done + off, ml - done);
+		zd_lane_copy(d + done, d - off, c);
+		done += c;
+	}
+}
+
+#define ZD_LANE_COPY_MAX 64u   // longer literal runs / matches are copied by the whole warp
+
 // Phase C: execute `cnt` (<= 32) sequences, one per lane.  Output and literal positions come from
-// warp scans; (a) all literal runs and (b) all matches whose source lies wholly before this batch's
-// output are independent and copied lane-parallel; (c) the remaining matches (sources inside the
-// batch, incl. overlapping ones) go in order, warp-cooperatively.
+// warp scans.  All literal runs are independent and copied first, lane-parallel.  Matches then go in
+// waves: a match is ready once every earlier match of the row that starts before its source's end
+// has been written (match starts grow with the lane, so that set is a prefix of the lanes); all ready
+// matches of a wave copy lane-parallel.  A row of n sequences takes (dependency depth) waves, not n
+// steps, and every wave is a few 16-byte round trips.
 ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte, u32 regen,
                        u32& lpos_io) {
 	u32 lane = zg_lane();
@@ -754,15 +796,17 @@ ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 cap, co
 	u32 btot = __shfl_sync(ZG_FULL, incl, 31), ltot = __shfl_sync(ZG_FULL, lincl, 31);
 	if (lpos + ltot > regen) return ZS_E_CORRUPT;
 	if (o + btot > cap) return ZS_E_DST_SMALL;
-	u64 mstart = o + (incl - ll - ml) + ll;  // where my match begins in the frame output
+	u32 rstart = incl - ml;          // my match's start relative to the row's output start
+	u64 mstart = o + rstart;         // ... and in the frame output
 	if (__any_sync(ZG_FULL, act && (u64)of > mstart)) return ZS_E_CORRUPT;
-	u8* d = out + mstart - ll;
+	u8* md = out + mstart;
+	u8* d = md - ll;
 	u32 lsrc = lpos + (lincl - ll);
 	// (a) literals
-	u32 longl = __ballot_sync(ZG_FULL, ll >= 48);
-	if (ll < 48) {
+	u32 longl = __ballot_sync(ZG_FULL, ll > ZD_LANE_COPY_MAX);
+	if (ll <= ZD_LANE_COPY_MAX) {
 		if (lit_rle) for (u32 k = 0; k < ll; k++) d[k] = (u8)rle_byte;
-		else for (u32 k = 0; k < ll; k++) d[k] = lit[lsrc + k];
+		else zd_lane_copy(d, lit + lsrc, ll);
 	}
 	while (longl) {
 		int l = __ffs((int)longl) - 1;
@@ -772,31 +816,39 @@ ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 cap, co
 		if (lit_rle) zg_warp_fill((u8*)(uintptr_t)d2, rle_byte, n2);
 		else zg_warp_copy((u8*)(uintptr_t)d2, lit + s2, n2);
 	}
-	// (b) independent matches
-	u8* md = out + mstart;
-	bool indep = act && ml > 0 && mstart - of + ml <= o;
-	u32 longm = __ballot_sync(ZG_FULL, indep && ml >= 48);
-	if (indep && ml < 48) {
-		const u8* ms = md - of;
-		for (u32 k = 0; k < ml; k++) md[k] = ms[k];
+	// (b) matches.  need = the lanes below me whose match starts before the end of my source
+	//     (rstart grows with the lane: binary search by shuffles; idle lanes sit at the far end)
+	i32 rs = act ? (i32)rstart : 0x7fffffff;
+	i32 send = (i32)rstart - (i32)of + (i32)zg_min<u32>(ml, of);  // <= 0: the source lies before this row
+	u32 nlow = 0;
+	ZG_UNROLL
+	for (int s = 16; s >= 1; s >>= 1) {
+		i32 v = __shfl_sync(ZG_FULL, rs, (int)(nlow + (u32)s - 1u));
+		if (v < send) nlow += (u32)s;
 	}
-	while (longm) {
-		int l = __ffs((int)longm) - 1;
-		longm &= longm - 1;
-		u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
-		u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
-		zg_warp_copy((u8*)(uintptr_t)d2, (const u8*)(uintptr_t)d2 - o2, n2);
-	}
-	__syncwarp();
-	// (c) dependent matches, in sequence order
-	u32 dep = __ballot_sync(ZG_FULL, act && ml > 0 && !indep);
-	while (dep) {
-		int l = __ffs((int)dep) - 1;
-		dep &= dep - 1;
-		u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
-		u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
-		zd_warp_match((u8*)(uintptr_t)d2, o2, n2);
+	nlow = zg_min<u32>(nlow, lane);
+	u32 need = (1u << nlow) - 1u;
+	u32 pending = __ballot_sync(ZG_FULL, act && ml > 0);
+	__syncwarp();  // the literals are written
+	while (pending) {
+		bool ready = ((pending >> lane) & 1u) && !(pending & need);
+		bool shortm = ml <= ZD_LANE_COPY_MAX;
+		u32 rdy = __ballot_sync(ZG_FULL, ready);
+		u32 longm = __ballot_sync(ZG_FULL, ready && !shortm);
+		if (ready && shortm) {
+			if (of >= ml) zd_lane_copy(md, md - of, ml);
+			else zd_lane_overlap(md, of, ml);
+		}
+		while (longm) {
+			int l = __ffs((int)longm) - 1;
+			longm &= longm - 1;
+			u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
+			u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
+			if (o2 >= n2) zg_warp_copy((u8*)(uintptr_t)d2, (const u8*)(uintptr_t)d2 - o2, n2);
+			else zd_warp_match((u8*)(uintptr_t)d2, o2, n2);
+		}
 		__syncwarp();
+		pending &= ~rdy;
 	}
 	o_io = o + btot;
 	lpos_io = lpos + ltot;
@@ -904,7 +956,10 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 				// a quarter of a warp's fair share of the input, but at least ZD_BATCH_BYTES
 				u64 cap = zg_max<u64>(ZD_BATCH_BYTES, archive_len / (4ull * gridDim.x * ZD_WARPS));
 				u64 fit = cap / (flen ? flen : 1);
-				want = (u32)zg_min<u64>(zg_min<u64>(32, zg_max<u64>(4, share)), zg_max<u64>(2, fit));
+				// ... and never so small that claiming a batch costs as much as decoding it (the smallest
+				// frames come last: they always go out as full rows)
+				u64 floor_b = (16u << 10) / (flen ? flen : 1);
+				want = (u32)zg_min<u64>(zg_min<u64>(32, zg_max<u64>(zg_max<u64>(4, share), floor_b)), zg_max<u64>(2, fit));
 				if (atomicCAS(queue, taken, taken + want) == taken) {
 					base = taken;
 					break;

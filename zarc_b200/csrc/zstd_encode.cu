@@ -741,14 +741,16 @@ ZG_DEV void ze_ld128(const u8* p, const u8* lim, u32 out[4]) {
 	ZG_UNROLL
 	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
 }
-// the same plus the four bytes before p (0 when p is within 4 bytes of the block start `lo`)
+// the same plus the four bytes before p (0 when p is within 4 bytes of the block start `lo`).
+// GUARD = false: the caller knows that p + 20 <= lim (no word can start at or beyond lim).
+template <bool GUARD>
 ZG_DEV u32 ze_ld128_prev(const u8* p, const u8* lo, const u8* lim, u32 out[4]) {
 	uintptr_t a = (uintptr_t)p;
 	const u32* w = (const u32*)(a & ~(uintptr_t)3);
 	u32 sh = (u32)(a & 3) * 8;
 	u32 x[5];
 	ZG_UNROLL
-	for (int k = 0; k < 5; k++) x[k] = (const u8*)(w + k) < lim ? w[k] : 0u;
+	for (int k = 0; k < 5; k++) x[k] = (!GUARD || (const u8*)(w + k) < lim) ? w[k] : 0u;
 	u32 xm = p >= lo + 4 ? w[-1] : 0u;
 	ZG_UNROLL
 	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
@@ -784,7 +786,10 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 		bool valid = pos + 4 <= n;
 		zg_prefetch_l2(src + zg_min<u32>(ip + 2048u, n - 1u));
 		u32 own[4];
-		u32 own_before = ze_ld128_prev(src + pos, src, lim, own);  // + the four bytes before this position
+		// away from the block's end (warp-uniform) no load of this window or of its candidates needs a bounds check
+		bool inner = ip + 52u <= n;
+		u32 own_before = inner ? ze_ld128_prev<false>(src + pos, src, lim, own)
+		                       : ze_ld128_prev<true>(src + pos, src, lim, own);  // + the four bytes before this position
 		u32 v = own[0];
 		u32 h = valid ? ze_hash4(v, hlog) : (0x80000000u | lane);
 		u32 te = valid ? htab[h] : 0;
@@ -807,7 +812,7 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 		u32 mlen = 0, bmatch = 0;
 		if (cand >= 0) {
 			u32 c[4];
-			u32 cand_before = ze_ld128_prev(src + cand, src, lim, c);
+			u32 cand_before = inner ? ze_ld128_prev<false>(src + cand, src, lim, c) : ze_ld128_prev<true>(src + cand, src, lim, c);
 			if (c[0] == v) {
 				u32 maxl = zg_min<u32>(n - pos, ZE_LANE_CAP);
 				mlen = ze_eq16(own, c);
@@ -1323,6 +1328,7 @@ struct ZeJob {
 	u32* codebuf;      // chunk staging: sequence codes (4 B per 4 input bytes)
 	u64* stbbuf;       // chunk staging: FSE state bits (8 B per 4 input bytes)
 	const u64* bounds; // [nchunks + 1] first block of every chunk
+	const u32* order;  // [nblocks] hand-out order: the blocks of each chunk, largest first (or null: index order)
 	u64 chunk_bytes;
 };
 struct ZeBlk {
@@ -1354,7 +1360,9 @@ ZG_DEV bool ze_next_block(const ZeJob& J, u32 chunk, u32* queue, u64& b) {
 	if (zg_lane() == 0) t = atomicAdd(queue, 1u);
 	t = __shfl_sync(ZG_FULL, t, 0);
 	b = J.bounds[chunk] + t;
-	return b < J.bounds[chunk + 1];
+	if (b >= J.bounds[chunk + 1]) return false;
+	if (J.order) b = J.order[b];
+	return true;
 }
 
 // first block of every chunk: chunk k holds the blocks whose staging offset is in [k, k+1) * chunk_bytes
@@ -1373,6 +1381,38 @@ __global__ void __launch_bounds__(128) k_ze_chunk_bounds(ZeJob J, u32 nchunks, u
 		else lo = mid + 1;
 	}
 	bounds[k] = lo;
+}
+
+// Hand-out order.  The queues give out blocks one at a time, and a warp needs milliseconds for a full
+// 128 KiB block but microseconds for a 1 KiB file: in index order each kernel would end with a tail as
+// long as its biggest block.  So the blocks of every chunk are handed out largest first (counting sort
+// by size, ZE_OBINS bins per chunk; the order inside a bin does not matter).
+#define ZE_OBINS 256u
+ZG_DEV u32 ze_obin(u32 n) { return ZE_OBINS - 1u - zg_min<u32>(n >> 9, ZE_OBINS - 1u); }
+ZG_DEV size_t ze_obin_slot(const ZeJob& J, const ZeBlk& B, u32 nchunks) {
+	return (size_t)zg_min<u64>(B.soff / J.chunk_bytes, nchunks - 1u) * ZE_OBINS + ze_obin(B.n);  // same chunk as k_ze_chunk_bounds
+}
+__global__ void __launch_bounds__(256) k_ze_order_count(ZeJob J, u32 nchunks, u32* bins) {
+	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= J.nblocks) return;
+	atomicAdd(&bins[ze_obin_slot(J, ze_locate(J, b), nchunks)], 1u);
+}
+// one warp per chunk: exclusive scan of its bins, starting at the chunk's first block
+__global__ void __launch_bounds__(32) k_ze_order_scan(ZeJob J, u32* bins) {
+	u32* c = bins + (size_t)blockIdx.x * ZE_OBINS;
+	u32 lane = threadIdx.x;
+	u32 run = (u32)J.bounds[blockIdx.x];
+	for (u32 k0 = 0; k0 < ZE_OBINS; k0 += 32) {
+		u32 v = c[k0 + lane];
+		u32 incl = zg_warp_incl_scan(v);
+		c[k0 + lane] = run + incl - v;
+		run += __shfl_sync(ZG_FULL, incl, 31);
+	}
+}
+__global__ void __launch_bounds__(256) k_ze_order_scatter(ZeJob J, u32 nchunks, u32* bins, u32* order) {
+	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= J.nblocks) return;
+	order[atomicAdd(&bins[ze_obin_slot(J, ze_locate(J, b), nchunks)], 1u)] = (u32)b;
 }
 
 // K2
@@ -1479,6 +1519,8 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	if (w.queue.reserve(qbytes) || w.meta.reserve(nblocks * sizeof(ZeBlkMeta)) || w.seqbuf.reserve(span * 2) || w.litbuf.reserve(span) ||
 	    w.codebuf.reserve(span) || w.stbbuf.reserve(span * 2) || w.bounds.reserve(((size_t)nchunks + 1) * 8))
 		return ZG_ERR(ZG_error_memory_allocation);
+	const bool sorted = nblocks > 8 && nblocks < 0xffffffffull;
+	if (sorted && (w.bins.reserve((size_t)nchunks * ZE_OBINS * 4) || w.order.reserve(nblocks * 4))) return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.queue.p, 0, qbytes, s);
 	ZeParams prm;
 	prm.lazy = level >= 3 ? 1 : 0;
@@ -1500,6 +1542,7 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	J.codebuf = w.codebuf.as<u32>();
 	J.stbbuf = w.stbbuf.as<u64>();
 	J.bounds = w.bounds.as<u64>();
+	J.order = nullptr;
 	J.chunk_bytes = chunk_bytes;
 	size_t smem_m = sizeof(ZeMatchWarp) * ZE_WARPS;
 	size_t smem_l = sizeof(ZeWarp) * ZE_WARPS;
@@ -1515,6 +1558,15 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	zg_prof_begin(ZG_K_ENCODE, s);
 	ZG_LAUNCH(k_ze_chunk_bounds, (nchunks + 128) / 128, 128, 0, s, J, nchunks, w.bounds.as<u64>());
 	ZG_COUNT_LAUNCH();
+	if (sorted) {
+		cudaMemsetAsync(w.bins.p, 0, (size_t)nchunks * ZE_OBINS * 4, s);
+		u32 g = (u32)((nblocks + 255) / 256);
+		ZG_LAUNCH(k_ze_order_count, g, 256, 0, s, J, nchunks, w.bins.as<u32>());
+		ZG_LAUNCH(k_ze_order_scan, nchunks, 32, 0, s, J, w.bins.as<u32>());
+		ZG_LAUNCH(k_ze_order_scatter, g, 256, 0, s, J, nchunks, w.bins.as<u32>(), w.order.as<u32>());
+		g_zg_launches += 3;
+		J.order = w.order.as<u32>();
+	}
 	u32* q = w.queue.as<u32>();
 	for (u32 k = 0; k < nchunks; k++) {
 		u32* qk = q + (size_t)k * ZE_NQ;
