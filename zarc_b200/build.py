@@ -80,7 +80,7 @@ def build_emu(force: bool = False) -> str:
     for src in _sources() + emu_src:
         o = os.path.join(OBJ, "emu", os.path.basename(src).rsplit(".", 1)[0] + ".o")
         objs.append(o)
-        cmd = ["g++", *flags, "-x", "c++", "-c", src, "-o", o]
+        cmd = ["g++", *flags, *os.environ.get("ZG_EMU_EXTRA", "").split(), "-x", "c++", "-c", src, "-o", o]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

@@ -2,6 +2,7 @@
 // Everything that touches content bytes is a CUDA kernel; the host code here only moves buffers
 // and does bookkeeping on sizes/offsets (frame/block *header* walks to find frame boundaries).
 #include "common.h"
+#include <mutex>
 #include <new>
 #include <vector>
 #include <string.h>
@@ -198,10 +199,21 @@ void zg_free_pinned(void* p) {
 // building blocks, device pointers
 size_t zg_blake3_batch_dev(void* stream, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n, uint8_t* digests) {
 	ZG_NEED_DEVICE();
-	ZgB3Work w;
-	size_t r = zg_blake3_run((cudaStream_t)stream, w, blob, off, len, n, digests);
+	// scratch (unit lists, scan tiles) is kept per device between calls: allocating it costs more than the kernels
+	static std::mutex mu;
+	static ZgB3Work cache[16];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 16) {
+		ZgB3Work w;
+		size_t r = zg_blake3_run((cudaStream_t)stream, w, blob, off, len, n, digests);
+		cudaStreamSynchronize((cudaStream_t)stream);
+		zg_b3work_free(w);
+		return r;
+	}
+	std::lock_guard<std::mutex> g(mu);
+	size_t r = zg_blake3_run((cudaStream_t)stream, cache[dev], blob, off, len, n, digests);
 	cudaStreamSynchronize((cudaStream_t)stream);
-	zg_b3work_free(w);
 	return r;
 }
 size_t zg_xxh64_batch_dev(void* stream, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n, uint64_t* hashes) {

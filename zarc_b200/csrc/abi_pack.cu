@@ -1,6 +1,9 @@
 // C ABI, pack side: zg_cctx (CCtx analogue + the Encoder's content state), zg_pack_batch[_dev],
 // zg_compress2.  Host code here only moves buffers and does bookkeeping on counts/sizes.
 #include "common.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include <string.h>
@@ -98,6 +101,9 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 	cudaStream_t s = c->stream;
 	if (frames_bytes) *frames_bytes = 0;
 	if (F == 0) return 0;
+	const bool trace = getenv("ZG_TRACE") != nullptr;
+	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double tc0 = now_ms();
 	u64 base = A.nfiles;
 	if (base + F >= 0xfffffff0ull) return ZG_ERR(ZG_error_GENERIC);
 	// the map's storage, indexed by global file id
@@ -143,6 +149,7 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 	ZG_CUDA(cudaMemcpyAsync(ht, totals, 24, cudaMemcpyDeviceToHost, s));
 	ZG_CUDA(cudaStreamSynchronize(s));
 	u64 nuniq = ht[0], nblocks = ht[1], comp_bytes = ht[2];
+	double tc1 = now_ms();
 	u32 flags = (c->checksum ? 1u : 0u) | (c->content_size ? 2u : 0u);
 	u64 new_offset = A.offset;
 	if (nuniq) {
@@ -170,6 +177,7 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 		ZG_CUDA(cudaMemcpyAsync(ht + 4, totals + 4, 8, cudaMemcpyDeviceToHost, s));
 		ZG_CUDA(cudaStreamSynchronize(s));
 		new_offset = ht[4];
+		if (trace) fprintf(stderr, "[zg pack]   digests+dedup+scans %.2f ms, encode+sizes %.2f ms\n", tc1 - tc0, now_ms() - tc1);
 		u64 bytes = new_offset - A.offset;
 		if (bytes > frames_cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
 		if (!frames_out) return ZG_ERR(ZG_error_dstBuffer_null);
@@ -370,16 +378,22 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 		ZG_CUDA(cudaEventRecord(st.in_done, c->s_in));
 		return 0;
 	};
+	const bool trace = getenv("ZG_TRACE") != nullptr;
+	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_begin = now_ms();
 	size_t r = upload(0);
 	u64 written = 0;
 	for (size_t k = 0; k < sl.size() && !zg_is_error(r); k++) {
 		const Slice& q = sl[k];
 		auto& st = c->stage[k & 1];
 		u64 m = q.i1 - q.i0;
+		double t0 = now_ms();
 		if (k + 1 < sl.size()) {
 			r = upload(k + 1);
 			if (zg_is_error(r)) break;
 		}
+		double t1 = now_ms();
+		if (trace) cudaStreamSynchronize(c->s_in), fprintf(stderr, "[zg pack] slice %zu: files %llu bytes %llu  upload(next) enqueue %.2f ms, in-stream drained at +%.2f ms\n", k, (unsigned long long)m, (unsigned long long)q.bytes, t1 - t0, now_ms() - t_begin);
 		u8* o = st.d_out_meta.as<u8>();
 		u64* d_foff = (u64*)o;
 		u64* d_flen = d_foff + m;
@@ -392,7 +406,9 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 			r = ZG_ERR(ZG_error_device);
 			break;
 		}
+		double t2 = now_ms();
 		r = pack_core(c, A, st.d_blob.as<u8>(), dm, dm + m, m, d_dig, d_first, d_foff, d_flen, st.d_frames.as<u8>(), cap, &bytes);
+		if (trace) fprintf(stderr, "[zg pack] slice %zu: core %.2f ms (ends at +%.2f ms)\n", k, now_ms() - t2, now_ms() - t_begin);
 		if (zg_is_error(r)) break;
 		// pack_core returns with the stream drained: the results can leave while the next slice computes
 		cudaError_t e = cudaSuccess;
@@ -409,6 +425,7 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 		written += bytes;
 	}
 	cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_out);
+	if (trace) fprintf(stderr, "[zg pack] all results on the host at +%.2f ms\n", now_ms() - t_begin);
 	if (zg_is_error(r)) return r;
 	if (e1 != cudaSuccess || e2 != cudaSuccess) return ZG_ERR(ZG_error_device);
 	if (frames_bytes) *frames_bytes = written;
