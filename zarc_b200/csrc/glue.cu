@@ -12,11 +12,23 @@ k_unpack_finalize(const u8* __restrict__ out, const u64* __restrict__ out_off, c
 	if (k >= n) return;
 	u32 st = status[k];
 	if (st == ZS_OK && produced[k] != ulen[k]) st = ZS_E_CORRUPT;
-	if (st == ZS_OK && verify && cksums[2 * k + 1]) {
+	if (st == ZS_OK && verify && cksums[2 * k + 1] && ulen[k] < XX_WARP_MIN) {
 		u64 h = xx_hash(out + out_off[k], ulen[k], 0);
 		if ((u32)h != cksums[2 * k]) st = ZS_E_CHECKSUM;
 	}
 	status[k] = st;
+}
+// the Content_Checksum of the frames of XX_WARP_MIN bytes and more, one warp per frame (xxh64.cuh); runs after
+// k_unpack_finalize, which has already settled the size check
+__global__ void __launch_bounds__(128)
+k_unpack_checksum_warp(const u8* __restrict__ out, const u64* __restrict__ out_off, const u64* __restrict__ ulen,
+                       const u32* __restrict__ cksums, u32* __restrict__ status, u64 n) {
+	__shared__ u64 sb[4][128];
+	u64 k = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (k >= n) return;
+	if (ulen[k] < XX_WARP_MIN || status[k] != ZS_OK || !cksums[2 * k + 1]) return;
+	u64 h = xx_hash_warp(out + out_off[k], ulen[k], sb[threadIdx.x >> 5]);
+	if ((threadIdx.x & 31) == 0 && (u32)h != cksums[2 * k]) status[k] = ZS_E_CHECKSUM;
 }
 
 // ok[k] = frame decoded and BLAKE3(out_k) == expected  (FrameIterator::verify, frame_iterator.rs:86-88)
@@ -42,6 +54,10 @@ size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off,
 	if (!n) return 0;
 	ZG_LAUNCH(k_unpack_finalize, (u32)((n + 127) / 128), 128, 0, s, out, out_off, ulen, produced, cksums, status, n, verify);
 	ZG_COUNT_LAUNCH();
+	if (verify) {
+		ZG_LAUNCH(k_unpack_checksum_warp, (u32)((n + 3) / 4), 128, 0, s, out, out_off, ulen, cksums, status, n);
+		ZG_COUNT_LAUNCH();
+	}
 	return 0;
 }
 size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n) {

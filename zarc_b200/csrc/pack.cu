@@ -207,7 +207,20 @@ k_xxh64_list(const u8* __restrict__ blob, const u64* __restrict__ off, const u64
 	u64 u = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (u >= nuniq) return;
 	u32 f = ulist[u];
+	if (len[f] >= XX_WARP_MIN) return;  // k_xxh64_list_warp's
 	out[u] = xx_hash(blob + off[f], len[f], 0);
+}
+// ... and one warp per unique file of XX_WARP_MIN bytes and more (xxh64.cuh)
+__global__ void __launch_bounds__(128)
+k_xxh64_list_warp(const u8* __restrict__ blob, const u64* __restrict__ off, const u64* __restrict__ len, const u32* __restrict__ ulist,
+                  u64 nuniq, u64* __restrict__ out) {
+	__shared__ u64 sb[4][128];
+	u64 u = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (u >= nuniq) return;
+	u32 f = ulist[u];
+	if (len[f] < XX_WARP_MIN) return;
+	u64 h = xx_hash_warp(blob + off[f], len[f], sb[threadIdx.x >> 5]);
+	if ((threadIdx.x & 31) == 0) out[u] = h;
 }
 
 // record the new frames in the encoder's map, then answer every file from the map
@@ -263,6 +276,8 @@ size_t zg_pk_frame_sizes(cudaStream_t s, const u32* ulist, const u64* blk_base, 
 }
 size_t zg_pk_xxh64_list(cudaStream_t s, const u8* blob, const u64* off, const u64* len, const u32* ulist, u64 nuniq, u64* out) {
 	ZG_LAUNCH(k_xxh64_list, PK_GRID(nuniq), 128, 0, s, blob, off, len, ulist, nuniq, out);
+	ZG_LAUNCH(k_xxh64_list_warp, (u32)((nuniq + 3) / 4), 128, 0, s, blob, off, len, ulist, nuniq, out);
+	ZG_COUNT_LAUNCH();
 	ZG_COUNT_LAUNCH();
 	return 0;
 }

@@ -88,3 +88,59 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 	}
 	return xx_finish(s, p + 32 * stripes, n, seed);
 }
+
+// Inputs of XX_WARP_MIN bytes and more are hashed by a whole warp.  The recurrence itself cannot be
+// split (each accumulator is a serial multiply-rotate chain over the stripes), but a single thread
+// also pays a memory round trip per 32-byte stripe; here the 32 lanes fetch 1 KiB (32 stripes) at a
+// time, coalesced and one chunk ahead, into shared memory, and lanes 0..3 run one accumulator each
+// from there: the chain's arithmetic latency is all that is left (~2 GB/s per input; many inputs run
+// side by side).  `sb`: 128 u64 of shared memory per warp.  All lanes call; all lanes get the hash.
+#define XX_WARP_MIN 8192u
+ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
+	u32 lane = zg_lane();
+	u64 acc = lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;  // seed 0
+	u64 chunks = n >> 10;
+	const u8* q = p + 32 * lane;
+	u64 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+	if (chunks) {
+		r0 = zg_ld64(q);
+		r1 = zg_ld64(q + 8);
+		r2 = zg_ld64(q + 16);
+		r3 = zg_ld64(q + 24);
+	}
+	for (u64 c = 0; c < chunks; c++) {
+		sb[4 * lane + 0] = r0;
+		sb[4 * lane + 1] = r1;
+		sb[4 * lane + 2] = r2;
+		sb[4 * lane + 3] = r3;
+		__syncwarp();
+		if (c + 1 < chunks) {  // in flight while the chains run
+			const u8* qn = q + ((c + 1) << 10);
+			r0 = zg_ld64(qn);
+			r1 = zg_ld64(qn + 8);
+			r2 = zg_ld64(qn + 16);
+			r3 = zg_ld64(qn + 24);
+		}
+		if (lane < 4) {
+			ZG_UNROLL
+			for (u32 i = 0; i < 32; i++) acc = xx_round(acc, sb[4 * i + lane]);
+		}
+		__syncwarp();
+	}
+	XxState s;
+	s.v1 = __shfl_sync(ZG_FULL, acc, 0);
+	s.v2 = __shfl_sync(ZG_FULL, acc, 1);
+	s.v3 = __shfl_sync(ZG_FULL, acc, 2);
+	s.v4 = __shfl_sync(ZG_FULL, acc, 3);
+	u64 h = 0;
+	if (lane == 0) {
+		const u8* t = p + (chunks << 10);
+		u64 stripes = (n >> 5) - (chunks << 5);  // < 32 left
+		for (u64 i = 0; i < stripes; i++) {
+			const u8* b = t + 32 * i;
+			xx_stripe(s, zg_ld64(b), zg_ld64(b + 8), zg_ld64(b + 16), zg_ld64(b + 24));
+		}
+		h = xx_finish(s, t + 32 * stripes, n, 0);
+	}
+	return __shfl_sync(ZG_FULL, h, 0);
+}
