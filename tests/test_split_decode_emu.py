@@ -1,0 +1,141 @@
+"""Block-parallel decoding of multi-block frames (zstd_decode.cu, k_zd_split_* / k_zd_join): frames whose blocks are
+independent (this library's encoder) decode block by block; any other frame is detected and decoded again serially.
+Either way the bytes equal the reference decoder's."""
+import ctypes as C
+import struct
+
+import numpy as np
+
+from oracle import ref_path
+from tests.golden.recipes import rand, text
+from tests.helpers import pack_batch, unpack_batch
+
+BLOCK = 128 * 1024
+
+
+def _b3(d):
+    import blake3
+
+    return blake3.blake3(d).digest()
+
+
+def _stats(lib):
+    out = (C.c_uint64 * 3)()
+    lib.dll.zg_internal_decode_stats(out)
+    return list(out)
+
+
+def _own_frames(lib, files, level=3):
+    cctx = lib.zg_cctx_create()
+    lib.check(lib.zg_cctx_init(cctx, level))
+    lib.check(lib.zg_cctx_set_parameter(cctx, 201, 1))
+    lib.check(lib.zg_cctx_reset_archive(cctx, 12))
+    r = pack_batch(lib, cctx, files)
+    lib.zg_cctx_free(cctx)
+    assert r["rc"] == 0
+    return [bytes(r["frames"][o - 12 : o - 12 + l]) for o, l in zip(r["off"], r["len"])]
+
+
+def _files():
+    return [text(300_000, 31), text(BLOCK + 1, 32), text(2 * BLOCK, 33), text(5000, 34), rand(3 * BLOCK + 77, 35),
+            text(200_000, 36) + bytes(150_000) + text(90_000, 37), b"", text(BLOCK, 38), text(1_000_000, 39)]
+
+
+def nblocks(n):
+    return max(1, -(-n // BLOCK))
+
+
+def test_own_multi_block_frames_decode_block_parallel(emu):
+    files = _files()
+    frames = _own_frames(emu, files)
+    outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], [_b3(f) for f in files])
+    assert rc == 0 and status == [0] * len(files)
+    assert outs == files and ok == [1] * len(files)
+    n_frames, n_items, n_redo = _stats(emu)
+    assert n_frames == len(files)
+    assert n_items == sum(nblocks(len(f)) for f in files)  # every block of every multi-block frame was its own item
+    assert n_redo == 0                                       # ... and none of them needed its neighbours
+    for f, fr in zip(files, frames):                         # the reference decoder agrees
+        assert ref_path.ref_decompress(fr, len(f)) == f
+
+
+def test_reference_multi_block_frames_fall_back_to_serial(emu):
+    files = _files()
+    for level in (1, 3, 19):
+        frames = [ref_path.ref_compress(f, level=level) for f in files]
+        outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], [_b3(f) for f in files])
+        assert rc == 0 and status == [0] * len(files)
+        assert outs == files and ok == [1] * len(files)
+        n_frames, n_items, n_redo = _stats(emu)
+        if level < 19:  # (level 19's block splitter makes blocks of other sizes: those frames are not even tried)
+            assert n_items > n_frames      # they were tried ...
+            assert n_redo >= 3             # ... and libzstd's text frames have matches across blocks
+
+
+def test_split_threshold_and_mixed_batch(emu):
+    files = _files()
+    own = _own_frames(emu, files)
+    ref = [ref_path.ref_compress(f) for f in files]
+    mixed = [own[i] if i % 2 else ref[i] for i in range(len(files))]
+    try:
+        for split_min in (0, 4 * BLOCK, 1 << 40):
+            emu.dll.zg_internal_set_decode_split_min(C.c_uint64(split_min))
+            outs, ok, status, rc = unpack_batch(emu, mixed, [len(f) for f in files], [_b3(f) for f in files])
+            assert rc == 0 and outs == files and ok == [1] * len(files)
+            if split_min == 1 << 40:
+                assert _stats(emu)[1] == len(files)  # nothing split
+    finally:
+        emu.dll.zg_internal_set_decode_split_min(C.c_uint64(0))
+
+
+def _raw_frame(parts, checksum=True):
+    """A frame of Raw blocks of the given sizes (single segment, 4-byte content size)."""
+    import xxhash
+
+    data = b"".join(parts)
+    out = bytearray(struct.pack("<IB", 0xFD2FB528, 0x80 | 0x20 | (4 if checksum else 0)) + struct.pack("<I", len(data)))
+    for i, p in enumerate(parts):
+        h = (len(p) << 3) | (1 if i + 1 == len(parts) else 0)
+        out += struct.pack("<I", h)[:3] + p
+    if checksum:
+        out += struct.pack("<I", xxhash.xxh64(data, seed=0).intdigest() & 0xFFFFFFFF)
+    return bytes(out), data
+
+
+def test_short_blocks_are_not_mistaken_for_full_ones(emu):
+    # two blocks, the first one short: the split guess (block 1 starts at 128 KiB) is wrong and must be noticed
+    f1, d1 = _raw_frame([rand(100_000, 1), rand(100_000, 2)])
+    # three blocks where ceil(n / 128 KiB) = 2: not split at all
+    f2, d2 = _raw_frame([rand(1000, 3), rand(BLOCK, 4), rand(70_000, 5)])
+    # full blocks: accepted
+    f3, d3 = _raw_frame([rand(BLOCK, 6), rand(BLOCK, 7), rand(5, 8)])
+    for f, d in ((f1, d1), (f2, d2), (f3, d3)):
+        assert ref_path.ref_decompress(f, len(d)) == d
+    outs, ok, status, rc = unpack_batch(emu, [f1, f2, f3], [len(d1), len(d2), len(d3)], [_b3(d1), _b3(d2), _b3(d3)])
+    assert rc == 0 and status == [0, 0, 0] and outs == [d1, d2, d3] and ok == [1, 1, 1]
+    n_frames, n_items, n_redo = _stats(emu)
+    assert (n_frames, n_items, n_redo) == (3, 2 + 1 + 3, 1)
+
+
+def test_corruption_inside_split_frames(emu):
+    files = [text(400_000, 41), text(300_000, 42), text(290_000, 43), text(10_000, 44)]
+    frames = _own_frames(emu, files)
+    bad_mid = bytearray(frames[0])
+    bad_mid[len(bad_mid) // 2] ^= 0x5A
+    bad_ck = bytearray(frames[1])
+    bad_ck[-2] ^= 1
+    truncated = frames[2][:-20]
+    batch = [bytes(bad_mid), bytes(bad_ck), truncated, frames[3], frames[0]]
+    sizes = [len(files[0]), len(files[1]), len(files[2]), len(files[3]), len(files[0])]
+    digs = [_b3(files[0]), _b3(files[1]), _b3(files[2]), _b3(files[3]), _b3(files[0])]
+    outs, ok, status, rc = unpack_batch(emu, batch, sizes, digs)
+    assert status[3] == 0 and status[4] == 0 and outs[3] == files[3] and outs[4] == files[0]
+    assert status[0] != 0 and status[2] != 0
+    assert status[1] == 22  # checksum_wrong
+    assert ok == [0, 0, 0, 1, 1]
+    for f, n, st in zip(batch, sizes, status):  # libzstd agrees on which frames are bad
+        try:
+            ref_path.ref_decompress(f, n)
+            assert st == 0
+        except ref_path.ZstdError:
+            assert st != 0

@@ -2,6 +2,9 @@
 // Everything that touches content bytes is a CUDA kernel; the host code here only moves buffers
 // and does bookkeeping on sizes/offsets (frame/block *header* walks to find frame boundaries).
 #include "common.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -138,7 +141,7 @@ static size_t unpack_core(zg_dctx* d, const u8* archive, u64 archive_len, u64 n,
 	}
 	ZG_TRY(zg_first_error_run(s, st, n, d->first.as<u64>()));
 	u64* hf = d->h_first.as<u64>();
-	ZG_CUDA(cudaMemcpyAsync(hf, d->first.p, 8, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(zg_publish(s, d->first.p, hf, 8));
 	ZG_CUDA(cudaStreamSynchronize(s));
 	ZG_CUDA(cudaGetLastError());
 	if (*hf != ~0ull) return ZG_ERR((size_t)(*hf & 0xff));
@@ -327,13 +330,7 @@ zg_dctx* zg_dctx_create(void) {
 void zg_dctx_free(zg_dctx* d) {
 	if (!d) return;
 	cudaStreamSynchronize(d->stream);
-	d->zd.lit.release();
-	d->zd.bins.release();
-	d->zd.perm.release();
-	d->zd.seqs.release();
-	d->zd.tabs.release();
-	d->zd.hufsave.release();
-	d->zd.queue.release();
+	d->zd.release();
 	zg_b3work_free(d->b3);
 	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->d_archive,
 	                 &d->d_meta, &d->d_out})
@@ -475,6 +472,9 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 		ZG_CUDA(cudaEventRecord(st.in_done, d->s_in));
 		return 0;
 	};
+	const bool trace = getenv("ZG_TRACE") != nullptr;
+	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_begin = now_ms();
 	size_t r = upload(0), first_err = 0;
 	for (size_t k = 0; k < sl.size() && !zg_is_error(r); k++) {
 		const Slice& q = sl[k];
@@ -492,8 +492,11 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 			r = ZG_ERR(ZG_error_device);
 			break;
 		}
+		double t2 = now_ms();
 		size_t rk = unpack_core(d, st.d_archive.as<u8>(), span, m, dm, dm + m, dm + 2 * m, d_dig, st.d_out.as<u8>(), ospan, dm + 3 * m,
 		                        d_dig ? d_okp : nullptr, d_status);
+		if (trace) fprintf(stderr, "[zg unpack] slice %zu: frames %llu out %llu  core starts +%.2f ms, takes %.2f ms\n", k, (unsigned long long)m,
+		                   (unsigned long long)q.obytes, t2 - t_begin, now_ms() - t2);
 		if (zg_is_error(rk)) {
 			if (zg_get_error_code(rk) == ZG_error_device || zg_get_error_code(rk) == ZG_error_memory_allocation) {
 				r = rk;
@@ -520,6 +523,7 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 		}
 	}
 	cudaError_t e1 = cudaStreamSynchronize(d->s_in), e2 = cudaStreamSynchronize(d->s_out);
+	if (trace) fprintf(stderr, "[zg unpack] all results on the host at +%.2f ms\n", now_ms() - t_begin);
 	if (zg_is_error(r)) return r;
 	if (e1 != cudaSuccess || e2 != cudaSuccess) return ZG_ERR(ZG_error_device);
 	return first_err;

@@ -146,7 +146,7 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 	ZG_TRY(zg_scan_run(s, c->tiles, c->nblk.as<u64>(), F, 0, c->blkfirst.as<u64>(), totals + 1));
 	ZG_TRY(zg_scan_run(s, c->tiles, c->clen.as<u64>(), F, 0, c->comp_off.as<u64>(), totals + 2));
 	u64* ht = c->h.as<u64>();
-	ZG_CUDA(cudaMemcpyAsync(ht, totals, 24, cudaMemcpyDeviceToHost, s));
+	ZG_CUDA(zg_publish(s, totals, ht, 24));
 	ZG_CUDA(cudaStreamSynchronize(s));
 	u64 nuniq = ht[0], nblocks = ht[1], comp_bytes = ht[2];
 	double tc1 = now_ms();
@@ -174,7 +174,7 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 		ZG_TRY(zg_pk_frame_sizes(s, c->ulist.as<u32>(), c->blk_base.as<u64>(), c->blk_pos.as<u64>(), totals + 3, len, nuniq, flags,
 		                         c->frame_len_u.as<u64>()));
 		ZG_TRY(zg_scan_run(s, c->tiles, c->frame_len_u.as<u64>(), nuniq, A.offset, c->frame_off_u.as<u64>(), totals + 4));
-		ZG_CUDA(cudaMemcpyAsync(ht + 4, totals + 4, 8, cudaMemcpyDeviceToHost, s));
+		ZG_CUDA(zg_publish(s, totals + 4, ht + 4, 8));
 		ZG_CUDA(cudaStreamSynchronize(s));
 		new_offset = ht[4];
 		if (trace) fprintf(stderr, "[zg pack]   digests+dedup+scans %.2f ms, encode+sizes %.2f ms\n", tc1 - tc0, now_ms() - tc1);

@@ -345,7 +345,7 @@ size_t zg_blake3_run(cudaStream_t s, ZgB3Work& w, const u8* blob, const u64* off
 	ZG_LAUNCH(k_blake3_unit_merge, (u32)((n + 255) / 256), 256, 0, s, w.ucount.as<u64>(), w.ubase.as<u64>(), n, w.unodes.as<u32>(), digests);
 	zg_prof_end(ZG_K_BLAKE3, s);
 	g_zg_launches += 3;
-	cudaMemcpyAsync(hcount, w.ctr.p, 12, cudaMemcpyDeviceToHost, s);
+	zg_publish(s, w.ctr.p, hcount, 12);
 	if (cudaStreamSynchronize(s) != cudaSuccess) return ZG_ERR(ZG_error_device);
 	u32 nmed = hcount[2];
 	if (nmed == 0) return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
@@ -354,7 +354,7 @@ size_t zg_blake3_run(cudaStream_t s, ZgB3Work& w, const u8* blob, const u64* off
 	ZG_LAUNCH(k_blake3_files, grid, B3_WARPS * 32, 0, s, blob, off, len, w.med.as<u32>(), (u64)nmed, digests, w.big.as<u64>(),
 	          w.ctr.as<u32>());
 	ZG_COUNT_LAUNCH();
-	cudaMemcpyAsync(hcount, w.ctr.p, 4, cudaMemcpyDeviceToHost, s);
+	zg_publish(s, w.ctr.p, hcount, 4);
 	if (cudaStreamSynchronize(s) != cudaSuccess) return ZG_ERR(ZG_error_device);
 	u32 nbig = *hcount;
 	if (nbig == 0) return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);

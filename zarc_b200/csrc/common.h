@@ -76,6 +76,7 @@ size_t zg_corpus_run(cudaStream_t s, u8* out, const u64* seg_off, const u32* seg
 
 // ---- scan.cu ----
 size_t zg_scan_run(cudaStream_t s, ZgBuf& tiles, const u64* in, u64 n, u64 base, u64* out, u64* total_out);
+cudaError_t zg_publish(cudaStream_t s, const void* dev_src, void* pinned_dst, u32 nbytes);  // small results -> pinned host memory, no copy engine
 
 // ---- zstd_decode.cu ----
 struct ZgZdWork {
@@ -84,7 +85,18 @@ struct ZgZdWork {
 	ZgBuf tabs;     // per-lane FSE decode-table slots
 	ZgBuf hufsave;  // per-lane Huffman weights (Treeless blocks)
 	ZgBuf queue;    // frame queue counter
-	ZgBuf bins, perm;  // size-sorted frame order
+	ZgBuf bins, perm;  // size-sorted hand-out order
+	// block-parallel decoding of multi-block frames: work items (a whole frame, or one block of a split frame)
+	ZgBuf nitems, ibase, tiles, total;  // per frame: item count and first item; scan scratch; totals {items, redo}
+	ZgBuf it_k, it_j, it_ip, it_len, it_status, it_prod;  // per item
+	ZgBuf tail, fabort, redo;  // per frame: offset past the last block, "a block failed" flag; frames to decode again serially
+	ZgHostBuf h;
+	void release() {
+		for (ZgBuf* b : {&seqs, &lit, &tabs, &hufsave, &queue, &bins, &perm, &nitems, &ibase, &tiles, &total, &it_k, &it_j, &it_ip, &it_len,
+		                 &it_status, &it_prod, &tail, &fabort, &redo})
+			b->release();
+		h.release();
+	}
 };
 size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
                           const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,

@@ -85,3 +85,19 @@ size_t zg_scan_run(cudaStream_t s, ZgBuf& tiles, const u64* in, u64 n, u64 base,
 	g_zg_launches += 3;
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
 }
+
+// A few bytes of results for the host, without the copy engine: a bulk D2H transfer of another stream (the
+// host-buffer API downloads one slice while the next one computes) would keep a small cudaMemcpyAsync
+// waiting behind it for milliseconds.  The kernel stores straight into pinned host memory (device-visible
+// under unified addressing); the caller synchronises the stream before reading.
+__global__ void __launch_bounds__(256) k_publish(const u8* __restrict__ src, volatile u8* host_dst, u32 nbytes) {
+	for (u32 i = threadIdx.x; i < nbytes; i += blockDim.x) host_dst[i] = src[i];
+#ifndef ZG_EMU
+	__threadfence_system();
+#endif
+}
+cudaError_t zg_publish(cudaStream_t s, const void* dev_src, void* pinned_dst, u32 nbytes) {
+	ZG_LAUNCH(k_publish, 1, 256, 0, s, (const u8*)dev_src, (volatile u8*)pinned_dst, nbytes);
+	ZG_COUNT_LAUNCH();
+	return cudaGetLastError();
+}

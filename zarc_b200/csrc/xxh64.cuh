@@ -109,10 +109,10 @@ ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 		r3 = zg_ld64(q + 24);
 	}
 	for (u64 c = 0; c < chunks; c++) {
-		sb[4 * lane + 0] = r0;
-		sb[4 * lane + 1] = r1;
-		sb[4 * lane + 2] = r2;
-		sb[4 * lane + 3] = r3;
+		sb[4 * lane + 0] = r0 * XXP2;  // the products are off the chain: all 32 lanes make them
+		sb[4 * lane + 1] = r1 * XXP2;
+		sb[4 * lane + 2] = r2 * XXP2;
+		sb[4 * lane + 3] = r3 * XXP2;
 		__syncwarp();
 		if (c + 1 < chunks) {  // in flight while the chains run
 			const u8* qn = q + ((c + 1) << 10);
@@ -123,7 +123,7 @@ ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 		}
 		if (lane < 4) {
 			ZG_UNROLL
-			for (u32 i = 0; i < 32; i++) acc = xx_round(acc, sb[4 * i + lane]);
+			for (u32 i = 0; i < 32; i++) acc = xx_rotl(acc + sb[4 * i + lane], 31) * XXP1;
 		}
 		__syncwarp();
 	}

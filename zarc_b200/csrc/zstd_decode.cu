@@ -57,12 +57,15 @@ struct ZdWarp {
 #define ZD_F_ML_DEF 512u
 #define ZD_F_OF_DEF 1024u
 #define ZD_F_HAS_CK 2048u   // checksum field was read
+#define ZD_F_ONEBLOCK 4096u // the item is one block of a split frame: decode it alone, then stop
+#define ZD_WHOLE 0xffffffffu  // item = the whole frame
 
 // one frame's decoding state; lives in the registers of the frame's lane
 struct ZdLane {
 	const u8* src;
 	u8* out;
 	u64 n, ip, cap, opos, fcs;
+	u64 base;           // lowest output position a match may reach (0; the block's start for a split frame's block)
 	u32 status, flags, fcs_len, cksum;
 	u32 rep0, rep1, rep2;
 	u32 ll_log, ml_log, of_log;
@@ -99,6 +102,7 @@ ZG_DEV ZdLane zd_bcast(const ZdLane& L, int f) {
 	U.ll_log = zd_bc(L.ll_log, f);
 	U.ml_log = zd_bc(L.ml_log, f);
 	U.of_log = zd_bc(L.of_log, f);
+	U.base = zd_bc(L.base, f);
 	U.blk = zd_bc(L.blk, f);
 	U.blk_n = zd_bc(L.blk_n, f);
 	U.nseq = zd_bc(L.nseq, f);
@@ -386,6 +390,7 @@ ZG_DEV void zd_fail(ZdLane& U, u32 code) {
 ZG_DEV void zd_frame_finish(ZdLane& U) {
 	U.flags &= ~ZD_F_ACTIVE;
 	U.nseq = U.nseq_left = 0;
+	if (U.flags & ZD_F_ONEBLOCK) return;  // the frame's end is checked when its blocks are joined
 	if (U.flags & ZD_F_CKSUM) {
 		if (U.ip + 4 > U.n) {
 			U.status = ZS_E_SRC_SIZE;
@@ -635,7 +640,7 @@ ZG_DEV void zd_setup_frame(ZdWarp* W, ZdLane& U, u32* slot, u32& arena_used, u8*
 	for (;;) {
 		if (U.ip + 3 > U.n) return zd_fail(U, ZS_E_SRC_SIZE);
 		u32 bh = zg_ld24(U.src + U.ip);
-		u32 last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+		u32 last = (bh & 1) | ((U.flags & ZD_F_ONEBLOCK) ? 1u : 0u), type = (bh >> 1) & 3, bsize = bh >> 3;
 		if (type == 3) return zd_fail(U, ZS_E_CORRUPT);
 		u64 body = U.ip + 3;
 		if (type == 0) {
@@ -719,7 +724,8 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 			}
 		}
 		// offsets beyond 2^28 exceed every window this decoder accepts; lengths are < 2^18 by construction
-		if (off > ZD_OFF_MAX) return false;
+		// (an offset of 0 only arises from the unknown repeat-offset history of a split frame's block: not independent)
+		if (off - 1u >= ZD_OFF_MAX) return false;
 		dst[k] = (u64)off | ((u64)ll << 28) | ((u64)ml << 46);
 	}
 	left -= cnt;
@@ -784,8 +790,8 @@ ZG_DEV void zd_lane_overlap(u8* d, u32 off, u32 ml) {
 // has been written (match starts grow with the lane, so that set is a prefix of the lanes); all ready
 // matches of a wave copy lane-parallel.  A row of n sequences takes (dependency depth) waves, not n
 // steps, and every wave is a few 16-byte round trips.
-ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte, u32 regen,
-                       u32& lpos_io) {
+ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 base, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte,
+                       u32 regen, u32& lpos_io) {
 	u32 lane = zg_lane();
 	u64 o = o_io;
 	u32 lpos = lpos_io;
@@ -798,7 +804,7 @@ ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 cap, co
 	if (o + btot > cap) return ZS_E_DST_SMALL;
 	u32 rstart = incl - ml;          // my match's start relative to the row's output start
 	u64 mstart = o + rstart;         // ... and in the frame output
-	if (__any_sync(ZG_FULL, act && (u64)of > mstart)) return ZS_E_CORRUPT;
+	if (__any_sync(ZG_FULL, act && (u64)of > mstart - base)) return ZS_E_CORRUPT;
 	u8* md = out + mstart;
 	u8* d = md - ll;
 	u32 lsrc = lpos + (lincl - ll);
@@ -867,7 +873,7 @@ ZG_DEV void zd_exec_block(ZdWarp* W, ZdLane& U, const u64* seqs, u8* litbuf, u8*
 	u64 o = U.opos;
 	u32 lpos = 0;
 	for (u32 s0 = 0; s0 < U.nseq; s0 += 32) {
-		r = zd_exec_row(seqs + s0, zg_min<u32>(32u, U.nseq - s0), U.out, o, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
+		r = zd_exec_row(seqs + s0, zg_min<u32>(32u, U.nseq - s0), U.out, o, U.base, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
 		if (r) return zd_fail(U, r);
 	}
 	// the literals after the last sequence
@@ -924,11 +930,150 @@ __global__ void __launch_bounds__(256) k_zd_bin_scatter(const u64* __restrict__ 
 	if (k < n) perm[atomicAdd(&bins[zd_bin(len[k])], 1u)] = (u32)k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block-parallel decoding of multi-block frames.
+// A frame is one serial chain of blocks for a general decoder (matches, repeat offsets and entropy
+// tables may refer to earlier blocks), and one warp decodes a frame at ~15 MB/s: a 4 GiB frame would
+// take minutes.  Frames written by this library's encoder have independent blocks (zstd_encode.cu),
+// and for those every block can be decoded on its own, knowing only where it starts: block j of a
+// frame whose blocks all regenerate 128 KiB starts at output position j * 128 KiB.  The decoder cannot
+// know who wrote a frame, so it speculates and verifies: frames longer than the split threshold have
+// their block headers walked (k_zd_split_*), every block becomes a work item (ZD_F_ONEBLOCK), and
+// k_zd_join accepts the frame only if every block decoded without touching anything outside itself and
+// produced exactly its share.  Any other frame (e.g. one made by libzstd, whose matches cross blocks)
+// goes on the redo list and is decoded again as a whole, serially -- the result is the same either way.
+struct ZdItems {
+	const u32* k;      // frame of the item (null: items are the frames themselves)
+	const u32* j;      // ZD_WHOLE or block index
+	const u64* ip;     // offset of the block header inside the frame
+	const u64* len;    // compressed bytes of the item (hand-out order and batching)
+	u32* status;       // per block item
+	u64* prod;         // per block item: bytes produced
+	u32* fabort;       // per frame: a block item failed, the rest need not be tried
+};
+
+// walk the block headers of frame k; returns the number of blocks if the frame can be split (content size
+// present and equal to ulen, block count == ceil(ulen / 128 KiB)), else 0.  emit != null: write the items.
+ZG_DEV u64 zd_split_walk(const u8* archive, u64 archive_len, u64 fo, u64 fl, u64 ul, u64 split_min, u32 k, u64 first, u32* it_k, u32* it_j,
+                         u64* it_ip, u64* it_len, u64* tail) {
+	if (ul < split_min || fo > archive_len || fl > archive_len - fo) return 0;
+	ZdLane L;
+	L.src = archive + fo;
+	L.n = fl;
+	L.status = ZS_OK;
+	L.flags = 0;
+	L.ip = L.fcs = 0;
+	L.fcs_len = 0;
+	zd_frame_header(L);
+	if (L.status != ZS_OK || L.fcs_len == 0 || L.fcs != ul) return 0;
+	u64 want = (ul + ZS_BLOCK_MAX - 1) / ZS_BLOCK_MAX;
+	if (want < 2 || want >= 0xffffff00ull) return 0;
+	u64 ip = L.ip, nb = 0;
+	for (;;) {
+		if (ip + 3 > fl) return 0;
+		u32 bh = zg_ld24(L.src + ip);
+		u32 last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+		if (type == 3 || bsize > ZS_BLOCK_MAX) return 0;
+		u64 body = type == 1 ? 1 : bsize;
+		if (ip + 3 + body > fl) return 0;
+		if (it_k) {
+			it_k[first + nb] = k;
+			it_j[first + nb] = (u32)nb;
+			it_ip[first + nb] = ip;
+			it_len[first + nb] = 3 + body;
+		}
+		nb++;
+		ip += 3 + body;
+		if (last) break;
+		if (nb >= want) return 0;
+	}
+	if (nb != want) return 0;
+	if (tail) tail[k] = ip;
+	return nb;
+}
+__global__ void __launch_bounds__(128)
+k_zd_split_count(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
+                 const u64* __restrict__ ulen, u64 n, u64 split_min, u64* __restrict__ nitems) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	u64 nb = zd_split_walk(archive, archive_len, off[k], len[k], ulen[k], split_min, (u32)k, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+	nitems[k] = nb ? nb : 1;
+}
+__global__ void __launch_bounds__(128)
+k_zd_split_emit(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
+                const u64* __restrict__ ulen, u64 n, u64 split_min, const u64* __restrict__ nitems, const u64* __restrict__ ibase, u32* it_k,
+                u32* it_j, u64* it_ip, u64* it_len, u64* tail, u32* fabort) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	fabort[k] = 0;
+	u64 first = ibase[k];
+	if (nitems[k] == 1) {
+		it_k[first] = (u32)k;
+		it_j[first] = ZD_WHOLE;
+		it_ip[first] = 0;
+		it_len[first] = len[k];
+		return;
+	}
+	zd_split_walk(archive, archive_len, off[k], len[k], ulen[k], split_min, (u32)k, first, it_k, it_j, it_ip, it_len, tail);
+}
+// one warp per frame: a split frame is accepted if all its blocks decoded and produced their exact share;
+// then its size / checksum fields are filled in as the serial decoder would; else it goes on the redo list
+__global__ void __launch_bounds__(128)
+k_zd_join(const u8* __restrict__ archive, const u64* __restrict__ off, const u64* __restrict__ len, const u64* __restrict__ ulen, u64 n,
+          const u64* __restrict__ nitems, const u64* __restrict__ ibase, const u32* __restrict__ it_status, const u64* __restrict__ it_prod,
+          const u64* __restrict__ tail, u32* status, u64* produced, u32* cksums, u32* redo, unsigned long long* redo_count) {
+	u64 k = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
+	u32 lane = threadIdx.x & 31;
+	if (k >= n) return;
+	u64 nb = nitems[k];
+	if (nb < 2) return;
+	u64 first = ibase[k], ul = ulen[k];
+	bool good = true;
+	for (u64 i = lane; i < nb; i += 32) {
+		u64 share = i + 1 < nb ? (u64)ZS_BLOCK_MAX : ul - (nb - 1) * ZS_BLOCK_MAX;
+		good = good && it_status[first + i] == ZS_OK && it_prod[first + i] == share;
+#ifdef ZG_EMU
+		if (getenv("ZG_DBG_JOIN") && !(it_status[first + i] == ZS_OK && it_prod[first + i] == share))
+			fprintf(stderr, "join: frame %llu block %llu status %u prod %llu share %llu\n", (unsigned long long)k, (unsigned long long)i, it_status[first + i], (unsigned long long)it_prod[first + i], (unsigned long long)share);
+#endif
+	}
+	good = __all_sync(ZG_FULL, good);
+	if (lane) return;
+	if (!good) {
+		redo[atomicAdd(redo_count, 1ull)] = (u32)k;
+		return;
+	}
+	const u8* src = archive + off[k];
+	u64 t = tail[k];
+	bool has_ck = (src[4] >> 2) & 1;
+	if (has_ck && t + 4 > len[k]) {
+		status[k] = ZS_E_SRC_SIZE;
+		produced[k] = 0;
+		cksums[2 * k] = cksums[2 * k + 1] = 0;
+		return;
+	}
+	status[k] = ZS_OK;
+	produced[k] = ul;
+	cksums[2 * k] = has_ck ? zg_ld32(src + t) : 0u;
+	cksums[2 * k + 1] = has_ck ? 1u : 0u;
+}
+// the redo list as whole-frame items
+__global__ void __launch_bounds__(128)
+k_zd_redo_items(const u32* __restrict__ redo, u64 nredo, const u64* __restrict__ len, u32* it_k, u32* it_j, u64* it_ip, u64* it_len) {
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nredo) return;
+	u32 k = redo[i];
+	it_k[i] = k;
+	it_j[i] = ZD_WHOLE;
+	it_ip[i] = 0;
+	it_len[i] = len[k];
+}
+
 __global__ void __launch_bounds__(ZD_WARPS * 32, ZD_MIN_CTAS)
 k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
                      const u64* __restrict__ ulen, const u64* __restrict__ out_off, u64 nframes, u8* out, u64 out_cap,
                      const u32* __restrict__ perm, u64* seq_arenas, u8* litbufs, u32* tabs, u8* hufsaves, u32* queue, u32* status,
-                     u64* produced, u32* cksums) {
+                     u64* produced, u32* cksums, ZdItems it) {
 	ZG_DYN_SMEM(ZdWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZdWarp* W = &sm[warp];
@@ -952,7 +1097,8 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 				}
 				u64 left = nframes - taken;
 				u64 share = left / (2ull * gridDim.x * ZD_WARPS);
-				u64 flen = len[perm ? perm[taken] : taken];
+				u32 t0 = perm ? perm[taken] : taken;
+				u64 flen = it.k ? it.len[t0] : len[t0];
 				// a quarter of a warp's fair share of the input, but at least ZD_BATCH_BYTES
 				u64 cap = zg_max<u64>(ZD_BATCH_BYTES, archive_len / (4ull * gridDim.x * ZD_WARPS));
 				u64 fit = cap / (flen ? flen : 1);
@@ -970,12 +1116,14 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 		want = __shfl_sync(ZG_FULL, want, 0);
 		if (base >= nframes) break;
 		bool mine = lane < want && (u64)base + lane < nframes;
-		u64 k = mine ? (perm ? (u64)perm[base + lane] : (u64)base + lane) : 0;
+		u64 t = mine ? (perm ? (u64)perm[base + lane] : (u64)base + lane) : 0;  // work item
+		u64 k = (mine && it.k) ? (u64)it.k[t] : t;                              // its frame
+		u32 jblk = (mine && it.k) ? it.j[t] : ZD_WHOLE;                         // ZD_WHOLE, or the block of a split frame
 		// ---- lane-private frame header ----
 		ZdLane L;
 		L.src = archive;
 		L.out = out;
-		L.n = L.ip = L.cap = L.opos = L.fcs = 0;
+		L.n = L.ip = L.cap = L.opos = L.fcs = L.base = 0;
 		L.status = ZS_OK;
 		L.flags = 0;
 		L.fcs_len = L.cksum = 0;
@@ -999,6 +1147,22 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 				L.cap = ul;
 				L.flags = ZD_F_ACTIVE;
 				zd_frame_header(L);
+				if (jblk != ZD_WHOLE && L.status == ZS_OK) {
+					// One block of a split frame, decoded on the assumption that the frame's blocks are
+					// independent of each other and each regenerates a full 128 KiB: it starts with an unknown
+					// (all-zero) repeat-offset history and no entropy tables, and may not reach below its own
+					// start.  Whatever breaks the assumption makes the item fail, and the frame is then
+					// decoded again serially (zg_zstd_decode_run).
+					if (it.fabort[k]) {
+						zd_fail(L, ZS_E_CORRUPT);  // a sibling block already failed
+					} else {
+						L.ip = it.ip[t];
+						L.opos = L.base = (u64)jblk * ZS_BLOCK_MAX;
+						L.cap = zg_min<u64>(L.cap, L.opos + ZS_BLOCK_MAX);
+						L.flags |= ZD_F_ONEBLOCK;
+						if (jblk) L.rep0 = L.rep1 = L.rep2 = 0;  // (the first block starts from the format's initial history)
+					}
+				}
 			}
 		}
 		__syncwarp();
@@ -1042,34 +1206,50 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 		}
 		if (mine) {
 			bool ok = L.status == ZS_OK;
-			status[k] = L.status;
-			produced[k] = ok ? L.opos : 0;
-			cksums[2 * k] = ok ? L.cksum : 0;
-			cksums[2 * k + 1] = (ok && (L.flags & ZD_F_HAS_CK)) ? 1u : 0u;
+			if (jblk == ZD_WHOLE) {
+				status[k] = L.status;
+				produced[k] = ok ? L.opos : 0;
+				cksums[2 * k] = ok ? L.cksum : 0;
+				cksums[2 * k + 1] = (ok && (L.flags & ZD_F_HAS_CK)) ? 1u : 0u;
+			} else {
+				it.status[t] = L.status;
+				it.prod[t] = ok ? L.opos - L.base : 0;
+				if (!ok) it.fabort[k] = 1u;
+			}
 		}
 		__syncwarp();
 	}
 }
 
-size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
-                          const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,
-                          u32* cksums) {
-	if (n == 0) return 0;
-	u64 batches = (n + 31) / 32;
+// frames of this many bytes and more are tried block-parallel (two blocks at least)
+static u64 g_zd_split_min = (u64)ZS_BLOCK_MAX + 1;
+extern "C" void zg_internal_set_decode_split_min(u64 v) { g_zd_split_min = v ? v : (u64)ZS_BLOCK_MAX + 1; }
+// what the last zg_zstd_decode_run did: {frames, work items, frames decoded again serially} (tests, tuning)
+static u64 g_zd_stats[3];
+extern "C" void zg_internal_decode_stats(u64 out[3]) {
+	for (int i = 0; i < 3; i++) out[i] = g_zd_stats[i];
+}
+
+// one launch of the decode kernel over `count` work items (frames when it.k is null), handed out largest first
+static size_t zd_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len, const u64* ulen,
+                        const u64* out_off, u64 count, u8* out, u64 out_cap, u32* status, u64* produced, u32* cksums, ZdItems it) {
+	if (count == 0) return 0;
+	if (count >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
+	u64 batches = (count + 31) / 32;
 	u32 grid = (u32)zg_min<u64>((batches + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * ZD_MIN_CTAS);
 	size_t warps = (size_t)grid * ZD_WARPS;
 	if (w.seqs.reserve(warps * ZD_SEQ_ARENA * 8) || w.lit.reserve(warps * ZD_LITBUF) || w.tabs.reserve(warps * 32 * ZD_TAB_SLOT * 4) ||
-	    w.hufsave.reserve(warps * 32 * ZD_HUFSAVE) || w.queue.reserve(16) || w.bins.reserve(ZD_BINS * 4) || w.perm.reserve(n * 4))
+	    w.hufsave.reserve(warps * 32 * ZD_HUFSAVE) || w.queue.reserve(16) || w.bins.reserve(ZD_BINS * 4) || w.perm.reserve(count * 4))
 		return ZG_ERR(ZG_error_memory_allocation);
-	if (n >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
 	cudaMemsetAsync(w.queue.p, 0, 16, s);
+	const u64* sort_len = it.k ? it.len : len;
 	const u32* perm = nullptr;
-	if (n > 64) {
+	if (count > 64) {
 		cudaMemsetAsync(w.bins.p, 0, ZD_BINS * 4, s);
-		u32 g = (u32)((n + 255) / 256);
-		ZG_LAUNCH(k_zd_bin_count, g, 256, 0, s, len, n, w.bins.as<u32>());
+		u32 g = (u32)((count + 255) / 256);
+		ZG_LAUNCH(k_zd_bin_count, g, 256, 0, s, sort_len, count, w.bins.as<u32>());
 		ZG_LAUNCH(k_zd_bin_scan, 1, 1024, 0, s, w.bins.as<u32>());
-		ZG_LAUNCH(k_zd_bin_scatter, g, 256, 0, s, len, n, w.bins.as<u32>(), w.perm.as<u32>());
+		ZG_LAUNCH(k_zd_bin_scatter, g, 256, 0, s, sort_len, count, w.bins.as<u32>(), w.perm.as<u32>());
 		ZG_COUNT_LAUNCH();
 		ZG_COUNT_LAUNCH();
 		ZG_COUNT_LAUNCH();
@@ -1083,9 +1263,63 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 		attr_set = true;
 	}
 	zg_prof_begin(ZG_K_DECODE, s);
-	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, smem, s, archive, archive_len, off, len, ulen, out_off, n, out, out_cap,
-	          perm, w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums);
+	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, smem, s, archive, archive_len, off, len, ulen, out_off, count, out, out_cap,
+	          perm, w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums, it);
 	zg_prof_end(ZG_K_DECODE, s);
 	ZG_COUNT_LAUNCH();
+	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
+}
+
+size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
+                          const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,
+                          u32* cksums) {
+	if (n == 0) return 0;
+	if (n >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
+	ZdItems none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	// which frames can be split into block items, and how many items that makes
+	if (w.nitems.reserve(n * 8) || w.ibase.reserve(n * 8) || w.total.reserve(16) || w.h.reserve(16)) return ZG_ERR(ZG_error_memory_allocation);
+	u32 g = (u32)((n + 127) / 128);
+	ZG_LAUNCH(k_zd_split_count, g, 128, 0, s, archive, archive_len, off, len, ulen, n, g_zd_split_min, w.nitems.as<u64>());
+	ZG_COUNT_LAUNCH();
+	u64* totals = w.total.as<u64>();
+	size_t r = zg_scan_run(s, w.tiles, w.nitems.as<u64>(), n, 0, w.ibase.as<u64>(), totals);
+	if (zg_is_error(r)) return r;
+	u64* h = w.h.as<u64>();
+	if (zg_publish(s, totals, h, 8) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+		return ZG_ERR(ZG_error_device);
+	u64 total = h[0];
+	g_zd_stats[0] = n;
+	g_zd_stats[1] = total;
+	g_zd_stats[2] = 0;
+	if (total == n)  // no multi-block frame that could be split: the items are the frames
+		return zd_launch(s, w, archive, archive_len, off, len, ulen, out_off, n, out, out_cap, status, produced, cksums, none);
+	if (total >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
+	if (w.it_k.reserve(total * 4) || w.it_j.reserve(total * 4) || w.it_ip.reserve(total * 8) || w.it_len.reserve(total * 8) ||
+	    w.it_status.reserve(total * 4) || w.it_prod.reserve(total * 8) || w.tail.reserve(n * 8) || w.fabort.reserve(n * 4) ||
+	    w.redo.reserve(n * 4))
+		return ZG_ERR(ZG_error_memory_allocation);
+	ZdItems it = {w.it_k.as<u32>(), w.it_j.as<u32>(), w.it_ip.as<u64>(), w.it_len.as<u64>(), w.it_status.as<u32>(), w.it_prod.as<u64>(),
+	              w.fabort.as<u32>()};
+	ZG_LAUNCH(k_zd_split_emit, g, 128, 0, s, archive, archive_len, off, len, ulen, n, g_zd_split_min, w.nitems.as<u64>(), w.ibase.as<u64>(),
+	          w.it_k.as<u32>(), w.it_j.as<u32>(), w.it_ip.as<u64>(), w.it_len.as<u64>(), w.tail.as<u64>(), w.fabort.as<u32>());
+	ZG_COUNT_LAUNCH();
+	r = zd_launch(s, w, archive, archive_len, off, len, ulen, out_off, total, out, out_cap, status, produced, cksums, it);
+	if (zg_is_error(r)) return r;
+	cudaMemsetAsync(totals + 1, 0, 8, s);
+	ZG_LAUNCH(k_zd_join, (u32)((n + 3) / 4), 128, 0, s, archive, off, len, ulen, n, w.nitems.as<u64>(), w.ibase.as<u64>(), w.it_status.as<u32>(),
+	          w.it_prod.as<u64>(), w.tail.as<u64>(), status, produced, cksums, w.redo.as<u32>(), (unsigned long long*)(totals + 1));
+	ZG_COUNT_LAUNCH();
+	if (zg_publish(s, totals + 1, h + 1, 8) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+		return ZG_ERR(ZG_error_device);
+	u64 nredo = h[1];
+	g_zd_stats[2] = nredo;
+	if (nredo) {
+		// frames whose blocks turned out to depend on each other: the whole frame again, in block order
+		ZG_LAUNCH(k_zd_redo_items, (u32)((nredo + 127) / 128), 128, 0, s, w.redo.as<u32>(), nredo, len, w.it_k.as<u32>(), w.it_j.as<u32>(),
+		          w.it_ip.as<u64>(), w.it_len.as<u64>());
+		ZG_COUNT_LAUNCH();
+		r = zd_launch(s, w, archive, archive_len, off, len, ulen, out_off, nredo, out, out_cap, status, produced, cksums, it);
+		if (zg_is_error(r)) return r;
+	}
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
 }
