@@ -341,7 +341,8 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 			cur.lo = off[i] < cur.lo ? off[i] : cur.lo;
 			cur.hi = off[i] + len[i] > cur.hi ? off[i] + len[i] : cur.hi;
 			cur.bytes += len[i];
-			if (cur.bytes >= g_zg_slice_bytes || i + 1 == n) {
+			// the first slice is a quarter of the others: its upload is the one transfer nothing overlaps
+			if (cur.bytes >= (sl.empty() ? g_zg_slice_bytes / 4 : g_zg_slice_bytes) || i + 1 == n) {
 				cur.i1 = i + 1;
 				sl.push_back(cur);
 				spans += cur.hi - cur.lo;
