@@ -34,7 +34,7 @@
 #define ZD_TAB_SLOT 1280u                // u32 entries per lane: LL 512 | ML 512 | OF 256
 #define ZD_HUFSAVE 272u                  // bytes per lane: 256 weights + count
 #define ZD_OFF_MAX ((1u << 28) - 1u)
-#define ZD_BATCH_BYTES (64u << 10)        // least compressed bytes per warp batch (see the hand-out in the kernel)
+#define ZD_BATCH_BYTES (128u << 10)        // least compressed bytes per warp batch (see the hand-out in the kernel)
 
 struct ZdWarp {
 	u32 tab[512];      // table under construction (FSE sequence table or Huffman-weight table)
@@ -1073,7 +1073,7 @@ __global__ void __launch_bounds__(ZD_WARPS * 32, ZD_MIN_CTAS)
 k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
                      const u64* __restrict__ ulen, const u64* __restrict__ out_off, u64 nframes, u8* out, u64 out_cap,
                      const u32* __restrict__ perm, u64* seq_arenas, u8* litbufs, u32* tabs, u8* hufsaves, u32* queue, u32* status,
-                     u64* produced, u32* cksums, ZdItems it) {
+                     u64* produced, u32* cksums, ZdItems it, u32 cap_div, u32 min_batch, u32 floor_bytes) {
 	ZG_DYN_SMEM(ZdWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZdWarp* W = &sm[warp];
@@ -1100,11 +1100,11 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 				u32 t0 = perm ? perm[taken] : taken;
 				u64 flen = it.k ? it.len[t0] : len[t0];
 				// a quarter of a warp's fair share of the input, but at least ZD_BATCH_BYTES
-				u64 cap = zg_max<u64>(ZD_BATCH_BYTES, archive_len / (4ull * gridDim.x * ZD_WARPS));
+				u64 cap = zg_max<u64>(min_batch, archive_len / ((u64)cap_div * gridDim.x * ZD_WARPS));
 				u64 fit = cap / (flen ? flen : 1);
 				// ... and never so small that claiming a batch costs as much as decoding it (the smallest
 				// frames come last: they always go out as full rows)
-				u64 floor_b = (16u << 10) / (flen ? flen : 1);
+				u64 floor_b = floor_bytes / (flen ? flen : 1);
 				want = (u32)zg_min<u64>(zg_min<u64>(32, zg_max<u64>(zg_max<u64>(4, share), floor_b)), zg_max<u64>(2, fit));
 				if (atomicCAS(queue, taken, taken + want) == taken) {
 					base = taken;
@@ -1230,6 +1230,15 @@ extern "C" void zg_internal_decode_stats(u64 out[3]) {
 	for (int i = 0; i < 3; i++) out[i] = g_zd_stats[i];
 }
 
+// hand-out tuning (see the kernel): a batch holds at most 1/cap_div of a warp's fair share of the input but at least
+// min_batch bytes; frames so small that 32 of them stay below floor_bytes always go out as full rows
+static u32 g_zd_tune[3] = {4, ZD_BATCH_BYTES, 32u << 10};
+extern "C" void zg_internal_set_decode_batching(u32 cap_div, u32 min_batch, u32 floor_bytes) {
+	g_zd_tune[0] = cap_div ? cap_div : 4;
+	g_zd_tune[1] = min_batch ? min_batch : ZD_BATCH_BYTES;
+	g_zd_tune[2] = floor_bytes ? floor_bytes : (32u << 10);
+}
+
 // one launch of the decode kernel over `count` work items (frames when it.k is null), handed out largest first
 static size_t zd_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len, const u64* ulen,
                         const u64* out_off, u64 count, u8* out, u64 out_cap, u32* status, u64* produced, u32* cksums, ZdItems it) {
@@ -1264,7 +1273,8 @@ static size_t zd_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 arch
 	}
 	zg_prof_begin(ZG_K_DECODE, s);
 	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, smem, s, archive, archive_len, off, len, ulen, out_off, count, out, out_cap,
-	          perm, w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums, it);
+	          perm, w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums, it,
+	          g_zd_tune[0], g_zd_tune[1], g_zd_tune[2]);
 	zg_prof_end(ZG_K_DECODE, s);
 	ZG_COUNT_LAUNCH();
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
