@@ -220,8 +220,12 @@ def main():
     lib = product_lib()
     assert lib.zg_device_count() > 0, "no CUDA device"
     lib.check(lib.zg_set_device(local_rank))
+    # rank 0's stdout carries exactly one JSON line: NCCL (version banner) and anything else that writes to fd 1 from
+    # native code goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout; rank 0's stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/zarc_bench_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -456,7 +460,8 @@ def main():
                               "pack_gbs": cpu["pack_gbs"], "unpack_gbs": cpu["unpack_gbs"]} if cpu else None),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     lib.zg_cctx_free(cctx)
     lib.zg_dctx_free(dctx)
     if world > 1:
