@@ -179,6 +179,7 @@ ZG_DEV_NOINLINE void ze_fse_build_ctable(const ZeCT& ct, const i16* norm, u32 ma
 	u32 log = ct.log, size = 1u << log;
 	u32 high = size - 1;
 	cumul[0] = 0;
+	ZG_UNROLL1
 	for (u32 s = 1; s <= maxsym + 1; s++) {
 		i32 n = norm[s - 1];
 		if (n == -1) {
@@ -189,18 +190,22 @@ ZG_DEV_NOINLINE void ze_fse_build_ctable(const ZeCT& ct, const i16* norm, u32 ma
 		}
 	}
 	u32 step = (size >> 1) + (size >> 3) + 3, mask = size - 1, pos = 0;
+	ZG_UNROLL1
 	for (u32 s = 0; s <= maxsym; s++)
+		ZG_UNROLL1
 		for (i32 i = 0; i < norm[s]; i++) {
 			tsym[pos] = (u8)s;
 			do {
 				pos = (pos + step) & mask;
 			} while (pos > high);
 		}
+	ZG_UNROLL1
 	for (u32 u = 0; u < size; u++) {
 		u32 s = tsym[u];
 		ct.st[cumul[s]++] = (u16)(size + u);
 	}
 	u32 total = 0;
+	ZG_UNROLL1
 	for (u32 s = 0; s <= maxsym; s++) {
 		i32 n = norm[s];
 		if (n == 0) {
@@ -232,6 +237,7 @@ ZG_DEV_NOINLINE void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 
 	u32 size = 1u << log;
 	i32 left = (i32)size;
 	u32 largest = 0, largest_p = 0;
+	ZG_UNROLL1
 	for (u32 s = 0; s <= maxsym; s++) {
 		u32 c = cnt[s];
 		if (c == 0) {
@@ -255,8 +261,10 @@ ZG_DEV_NOINLINE void ze_fse_normalize(i16* norm, const u32* cnt, u32 total, u32 
 		return;
 	}
 	// rare: too many forced-to-1 symbols.  Take the excess from the largest entries, one at a time.
+	ZG_UNROLL1
 	while (left < 0) {
 		u32 big = 0;
+		ZG_UNROLL1
 		for (u32 s = 1; s <= maxsym; s++)
 			if (norm[s] > norm[big]) big = s;
 		norm[big]--;
@@ -357,6 +365,7 @@ ZG_DEV_NOINLINE u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 m
 	ze_bw_add(w, log - 5, 4);
 	i32 remaining = 1 << log;
 	u32 s = 0;
+	ZG_UNROLL1
 	while (remaining > 0 && s <= maxsym) {
 		u32 bits = zs_highbit((u32)remaining + 1) + 1;
 		u32 thr = (1u << bits) - 1u - ((u32)remaining + 1u);
@@ -373,8 +382,10 @@ ZG_DEV_NOINLINE u32 ze_fse_write_ncount(u8* dst, u32 cap, const i16* norm, u32 m
 		if (zero) {
 			// count the zero symbols that follow, in 2-bit groups (3 = "three more, keep going")
 			u32 run = 0;
+			ZG_UNROLL1
 			while (s + run <= maxsym && norm[s + run] == 0) run++;
 			s += run;
+			ZG_UNROLL1
 			while (run >= 3) {
 				ze_bw_add(w, 3, 2);
 				run -= 3;
@@ -398,6 +409,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	u32 lane = zg_lane();
 	// present symbols, ascending symbol order -> node_cnt/node_par as (cnt, sym) staging
 	u32 n = 0;
+	ZG_UNROLL1
 	for (u32 k = 0; k < 8; k++) {
 		u32 s = k * 32 + lane;
 		u32 c = W->hist[s];
@@ -414,9 +426,11 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	if (n < 2) return 0;
 	u32 maxsym = e.node_par[256 + n - 1];
 	// rank sort by (count, symbol)
+	ZG_UNROLL1
 	for (u32 i = lane; i < n; i += 32) {
 		u32 key = (e.node_cnt[256 + i] << 8) | e.node_par[256 + i];
 		u32 rank = 0;
+		ZG_UNROLL1
 		for (u32 j = 0; j < n; j++) rank += ((e.node_cnt[256 + j] << 8) | e.node_par[256 + j]) < key;
 		e.sorted_cnt[rank] = key >> 8;
 		e.sorted_sym[rank] = (u16)(key & 0xff);
@@ -424,9 +438,12 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	__syncwarp();
 	if (lane == 0) {
 		u32 maxd = 0;
+		ZG_UNROLL1
 		for (u32 limit = 1;; limit <<= 1) {
+			ZG_UNROLL1
 			for (u32 i = 0; i < n; i++) e.node_cnt[i] = zg_max<u32>(e.sorted_cnt[i], limit);
 			u32 q1 = 0, q2 = n, nn = n;
+			ZG_UNROLL1
 			while (nn < 2 * n - 1) {
 				u32 a, b;
 				if (q1 < n && (q2 >= nn || e.node_cnt[q1] <= e.node_cnt[q2])) a = q1++;
@@ -440,6 +457,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 			}
 			e.node_depth[2 * n - 2] = 0;
 			maxd = 0;
+			ZG_UNROLL1
 			for (i32 k = (i32)(2 * n - 3); k >= 0; k--) {
 				u32 d = e.node_depth[e.node_par[k]] + 1u;
 				e.node_depth[k] = (u8)d;
@@ -449,7 +467,9 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 		}
 		// weights and canonical codes (ascending weight, then ascending symbol: RFC 8878 §4.2.1)
 		u32 rank[13];
+		ZG_UNROLL1
 		for (u32 w = 0; w < 13; w++) rank[w] = 0;
+		ZG_UNROLL1
 		for (u32 i = 0; i < n; i++) {
 			u32 w = maxd + 1 - e.node_depth[i];
 			e.hweight[e.sorted_sym[i]] = (u8)w;
@@ -457,10 +477,12 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 		}
 		u32 next[13];
 		u32 start = 0;
+		ZG_UNROLL1
 		for (u32 w = 1; w <= maxd; w++) {
 			next[w] = start >> (w - 1);
 			start += rank[w] << (w - 1);
 		}
+		ZG_UNROLL1
 		for (u32 s = 0; s <= maxsym; s++) {
 			u32 w = e.hweight[s];
 			if (w) {
@@ -483,13 +505,16 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 	u32 fse_size = 0;
 	if (nw > 2) {
 		u32 cnt[13];
+		ZG_UNROLL1
 		for (u32 i = 0; i < 13; i++) cnt[i] = 0;
 		u32 maxw = 0, maxc = 0;
+		ZG_UNROLL1
 		for (u32 i = 0; i < nw; i++) {
 			u32 w = e.hweight[i];
 			cnt[w]++;
 			if (w > maxw) maxw = w;
 		}
+		ZG_UNROLL1
 		for (u32 i = 0; i <= maxw; i++) maxc = zg_max<u32>(maxc, cnt[i]);
 		if (maxc != nw && maxc > 1) {
 			u32 log = ze_fse_table_log(6, nw, maxw);
@@ -510,6 +535,7 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 					s2 = ze_fse_init_state(ct, e.hweight[--ip]);
 					s1 = ze_fse_init_state(ct, e.hweight[--ip]);
 				}
+				ZG_UNROLL1
 				while (ip > 0) {
 					ze_fse_encode(bw, ct, s2, e.hweight[--ip]);
 					ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
@@ -528,6 +554,7 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 	}
 	if (!direct) return 0;
 	e.wdesc[0] = (u8)(127 + nw);
+	ZG_UNROLL1
 	for (u32 i = 0; i < nw; i += 2) {
 		u32 hi = e.hweight[i], lo = i + 1 < nw ? e.hweight[i + 1] : 0;
 		e.wdesc[1 + (i >> 1)] = (u8)((hi << 4) | lo);
