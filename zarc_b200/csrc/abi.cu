@@ -11,8 +11,15 @@
 #include <string.h>
 
 uint64_t g_zg_launches = 0;
+// Slices of the host-buffer API.  Unpack wants ~100 K frames in flight per launch (1 GiB of C2-shaped output); the
+// encoder's kernels keep their efficiency on less, and smaller pack slices expose less of the first upload.
 uint64_t g_zg_slice_bytes = 1024ull << 20;
-extern "C" void zg_internal_set_slice_bytes(uint64_t v) { g_zg_slice_bytes = v ? v : (1024ull << 20); }
+uint64_t g_zg_pack_slice_bytes = 768ull << 20;
+extern "C" void zg_internal_set_slice_bytes(uint64_t v) {
+	g_zg_slice_bytes = v ? v : (1024ull << 20);
+	g_zg_pack_slice_bytes = v ? v : (768ull << 20);
+}
+extern "C" void zg_internal_set_pack_slice_bytes(uint64_t v) { g_zg_pack_slice_bytes = v ? v : (768ull << 20); }
 
 static int g_dev_count = -2;
 static int g_sm_count = 0;

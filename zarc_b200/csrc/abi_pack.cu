@@ -310,7 +310,7 @@ size_t zg_pack_batch_dev(zg_cctx* c, const uint8_t* blob, const uint64_t* off, c
 	return pack_core(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes);
 }
 
-// Host-buffer pack.  The batch is cut into slices of about g_zg_slice_bytes of input (in file order) that
+// Host-buffer pack.  The batch is cut into slices of about g_zg_pack_slice_bytes of input (in file order) that
 // go through two staging sets: while the kernels of slice k run on the context's stream, slice k+1
 // is already on its way up (s_in) and the frames of slice k-1 are on their way down (s_out).  The
 // archive state (dedup map, running offset) carries from slice to slice exactly as it does from call
@@ -342,7 +342,7 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 			cur.hi = off[i] + len[i] > cur.hi ? off[i] + len[i] : cur.hi;
 			cur.bytes += len[i];
 			// the first slice is a quarter of the others: its upload is the one transfer nothing overlaps
-			if (cur.bytes >= (sl.empty() ? g_zg_slice_bytes / 4 : g_zg_slice_bytes) || i + 1 == n) {
+			if (cur.bytes >= (sl.empty() ? g_zg_pack_slice_bytes / 4 : g_zg_pack_slice_bytes) || i + 1 == n) {
 				cur.i1 = i + 1;
 				sl.push_back(cur);
 				spans += cur.hi - cur.lo;

@@ -5,7 +5,7 @@
 
 #define ZG_ERR(code) ((size_t)0 - (size_t)(code))
 
-extern uint64_t g_zg_slice_bytes;  // host-buffer API: input bytes per pipelined slice (tests shrink it)
+extern uint64_t g_zg_slice_bytes, g_zg_pack_slice_bytes;  // host-buffer API: bytes per pipelined slice, unpack / pack (tests shrink them)
 extern uint64_t g_zg_launches;  // kernels launched by this library (bench.py's gpu_launches)
 #define ZG_COUNT_LAUNCH() (++g_zg_launches)
 
