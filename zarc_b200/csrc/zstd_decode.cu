@@ -682,20 +682,22 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 	u32 sl = L.sl, so = L.so, sm = L.sm;
 	u32 rep0 = L.rep0, rep1 = L.rep1, rep2 = L.rep2;
 	u32 left = L.nseq_left;
+	u32 bad = 0;  // checked once per call: a bad sequence only poisons values, never an address (states stay inside their tables)
 	for (u32 k = 0; k < cnt; k++) {
 		u32 oe = oft[so], me = mlt[sm], le = llt[sl];
-		u32 oc = oe & 0xff, mc = me & 0xff, lc = le & 0xff;
-		if (oc > 31 || mc > 52 || lc > 35) return false;
 		zs_back_reload(b);  // >= 57 bits available from here
+		// the codes come out of tables whose symbols were range-checked when they were read (zd_seq_table)
+		u32 oc = oe & 0xff;
+		u32 mp = ZS_ML_PACK[me & 0xff], lp = ZS_LL_PACK[le & 0xff];
 		u32 ofv = (1u << oc) + zs_back_read(b, oc);
 		u32 used = oc;
 		if (oc > 24) {
 			zs_back_reload(b);
 			used = 0;
 		}
-		u32 mb = ZS_ML_BITS[mc], lb = ZS_LL_BITS[lc];
-		u32 ml = ZS_ML_BASE[mc] + zs_back_read(b, mb);
-		u32 ll = ZS_LL_BASE[lc] + zs_back_read(b, lb);
+		u32 mb = mp >> 24, lb = lp >> 24;
+		u32 ml = (mp & 0xffffffu) + zs_back_read(b, mb);
+		u32 ll = (lp & 0xffffffu) + zs_back_read(b, lb);
 		used += mb + lb;
 		if (left - k > 1) {
 			if (used > 30) zs_back_reload(b);  // the three state updates need <= 26 bits
@@ -703,7 +705,6 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 			sm = (me >> 16) + zs_back_read(b, (me >> 8) & 0xff);
 			so = (oe >> 16) + zs_back_read(b, (oe >> 8) & 0xff);
 		}
-		if (zs_back_overflow(b)) return false;
 		// repeat-offset resolution (RFC 8878 §3.1.1.5)
 		u32 off;
 		if (ofv > 3) {
@@ -713,21 +714,20 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 			rep0 = off;
 		} else {
 			u32 idx = ofv - 1 + (ll == 0 ? 1 : 0);
-			if (idx == 0) {
-				off = rep0;
-			} else {
-				off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-				if (off == 0) return false;
-				if (idx > 1) rep2 = rep1;
+			off = idx == 0 ? rep0 : idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1u;
+			if (idx > 1) rep2 = rep1;
+			if (idx > 0) {
 				rep1 = rep0;
 				rep0 = off;
 			}
 		}
-		// offsets beyond 2^28 exceed every window this decoder accepts; lengths are < 2^18 by construction
-		// (an offset of 0 only arises from the unknown repeat-offset history of a split frame's block: not independent)
-		if (off - 1u >= ZD_OFF_MAX) return false;
+		// offsets beyond 2^28 exceed every window this decoder accepts; an offset of 0 only arises from a corrupt stream
+		// or from the unknown repeat-offset history of a split frame's block (then the block is not independent);
+		// lengths are < 2^18 by construction
+		bad |= (off - 1u >= ZD_OFF_MAX) ? 1u : 0u;
 		dst[k] = (u64)off | ((u64)ll << 28) | ((u64)ml << 46);
 	}
+	if (bad || zs_back_overflow(b)) return false;
 	left -= cnt;
 	if (left == 0) {
 		zs_back_reload(b);
