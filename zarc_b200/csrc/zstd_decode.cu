@@ -682,17 +682,19 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 	u32 sl = L.sl, so = L.so, sm = L.sm;
 	u32 rep0 = L.rep0, rep1 = L.rep1, rep2 = L.rep2;
 	u32 left = L.nseq_left;
+	ZsBelow ahead = {0, 0};
+	zs_below_fetch(b, ahead);
 	u32 bad = 0;  // checked once per call: a bad sequence only poisons values, never an address (states stay inside their tables)
 	for (u32 k = 0; k < cnt; k++) {
 		u32 oe = oft[so], me = mlt[sm], le = llt[sl];
-		zs_back_reload(b);  // >= 57 bits available from here
+		zs_back_reload_ahead(b, ahead);  // >= 57 bits available from here; no memory wait (the bytes came in a step ago)
 		// the codes come out of tables whose symbols were range-checked when they were read (zd_seq_table)
 		u32 oc = oe & 0xff;
 		u32 mp = ZS_ML_PACK[me & 0xff], lp = ZS_LL_PACK[le & 0xff];
 		u32 ofv = (1u << oc) + zs_back_read(b, oc);
 		u32 used = oc;
 		if (oc > 24) {
-			zs_back_reload(b);
+			zs_back_reload_ahead(b, ahead);
 			used = 0;
 		}
 		u32 mb = mp >> 24, lb = lp >> 24;
@@ -700,7 +702,7 @@ ZG_DEV bool zd_lane_decode(ZdLane& L, u32 cnt, const u32* llt, const u32* mlt, c
 		u32 ll = (lp & 0xffffffu) + zs_back_read(b, lb);
 		used += mb + lb;
 		if (left - k > 1) {
-			if (used > 30) zs_back_reload(b);  // the three state updates need <= 26 bits
+			if (used > 30) zs_back_reload_ahead(b, ahead);  // the three state updates need <= 26 bits
 			sl = (le >> 16) + zs_back_read(b, (le >> 8) & 0xff);
 			sm = (me >> 16) + zs_back_read(b, (me >> 8) & 0xff);
 			so = (oe >> 16) + zs_back_read(b, (oe >> 8) & 0xff);
@@ -790,13 +792,13 @@ ZG_DEV void zd_lane_overlap(u8* d, u32 off, u32 ml) {
 // has been written (match starts grow with the lane, so that set is a prefix of the lanes); all ready
 // matches of a wave copy lane-parallel.  A row of n sequences takes (dependency depth) waves, not n
 // steps, and every wave is a few 16-byte round trips.
-ZG_DEV u32 zd_exec_row(const u64* seqs, u32 cnt, u8* out, u64& o_io, u64 base, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte,
+ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, u8* out, u64& o_io, u64 base, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte,
                        u32 regen, u32& lpos_io) {
 	u32 lane = zg_lane();
 	u64 o = o_io;
 	u32 lpos = lpos_io;
 	bool act = lane < cnt;
-	u64 sq = act ? seqs[lane] : 0;
+	u64 sq = act ? sq_lane : 0;
 	u32 of = (u32)sq & ZD_OFF_MAX, ll = (u32)(sq >> 28) & 0x3ffffu, ml = (u32)(sq >> 46);
 	u32 incl = zg_warp_incl_scan(ll + ml), lincl = zg_warp_incl_scan(ll);
 	u32 btot = __shfl_sync(ZG_FULL, incl, 31), ltot = __shfl_sync(ZG_FULL, lincl, 31);
@@ -872,9 +874,13 @@ ZG_DEV void zd_exec_block(ZdWarp* W, ZdLane& U, const u64* seqs, u8* litbuf, u8*
 	if (r) return zd_fail(U, r);
 	u64 o = U.opos;
 	u32 lpos = 0;
+	u32 lane = zg_lane();
+	u64 sq = lane < U.nseq ? seqs[lane] : 0;
 	for (u32 s0 = 0; s0 < U.nseq; s0 += 32) {
-		r = zd_exec_row(seqs + s0, zg_min<u32>(32u, U.nseq - s0), U.out, o, U.base, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
+		u64 sq_next = s0 + 32 + lane < U.nseq ? seqs[s0 + 32 + lane] : 0;  // the next row's records come in while this row executes
+		r = zd_exec_row(sq, zg_min<u32>(32u, U.nseq - s0), U.out, o, U.base, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
 		if (r) return zd_fail(U, r);
+		sq = sq_next;
 	}
 	// the literals after the last sequence
 	u32 rest = h.regen - lpos;
@@ -1082,6 +1088,8 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 	u8* litbuf = litbufs + gw * ZD_LITBUF;
 	u32* my_slot = tabs + (gw * 32 + lane) * ZD_TAB_SLOT;
 	u8* hufsave0 = hufsaves + gw * 32 * ZD_HUFSAVE;
+	u64 hint_len = ~0ull;  // compressed size of the last item of this warp's previous batch
+	u64 prev_base = 0;
 	for (;;) {
 		// Hand-out: frames come largest first.  A batch is up to 32 frames, but (a) no more than about
 		// ZD_BATCH_BYTES of compressed input -- the phases around the lane-parallel sequence decode run
@@ -1089,32 +1097,29 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 		// and (b) smaller towards the end, so that the last round is spread over all warps.
 		u32 base = 0, want = 32;
 		if (lane == 0) {
-			for (;;) {
-				u32 taken = *(volatile u32*)queue;
-				if (taken >= nframes) {
-					base = taken;
-					break;
-				}
-				u64 left = nframes - taken;
-				u64 share = left / (2ull * gridDim.x * ZD_WARPS);
-				u32 t0 = perm ? perm[taken] : taken;
-				u64 flen = it.k ? it.len[t0] : len[t0];
-				// a quarter of a warp's fair share of the input, but at least ZD_BATCH_BYTES
-				u64 cap = zg_max<u64>(min_batch, archive_len / ((u64)cap_div * gridDim.x * ZD_WARPS));
-				u64 fit = cap / (flen ? flen : 1);
-				// ... and never so small that claiming a batch costs as much as decoding it (the smallest
-				// frames come last: they always go out as full rows)
-				u64 floor_b = floor_bytes / (flen ? flen : 1);
-				want = (u32)zg_min<u64>(zg_min<u64>(32, zg_max<u64>(zg_max<u64>(4, share), floor_b)), zg_max<u64>(2, fit));
-				if (atomicCAS(queue, taken, taken + want) == taken) {
-					base = taken;
-					break;
-				}
+			// The batch size comes from the size of the last item this warp saw (items come largest first, so it
+			// bounds every later one) and from this warp's previous position in the queue: nothing has to be read
+			// before the claim, and the claim is one atomicAdd -- no compare-and-swap loop for ~3000 warps to fight over.
+			u64 flen = hint_len;
+			if (flen == ~0ull) {
+				u32 t0 = perm ? perm[0] : 0u;
+				flen = it.k ? it.len[t0] : len[t0];
 			}
+			u64 left = nframes > prev_base ? nframes - prev_base : 1;
+			u64 share = left / (2ull * gridDim.x * ZD_WARPS);
+			// a quarter of a warp's fair share of the input, but at least min_batch bytes
+			u64 cap = zg_max<u64>(min_batch, archive_len / ((u64)cap_div * gridDim.x * ZD_WARPS));
+			u64 fit = cap / (flen ? flen : 1);
+			// ... and never so small that claiming a batch costs as much as decoding it (the smallest
+			// frames come last: they always go out as full rows)
+			u64 floor_b = floor_bytes / (flen ? flen : 1);
+			want = (u32)zg_min<u64>(zg_min<u64>(32, zg_max<u64>(zg_max<u64>(4, share), floor_b)), zg_max<u64>(2, fit));
+			base = atomicAdd(queue, want);
 		}
 		base = __shfl_sync(ZG_FULL, base, 0);
 		want = __shfl_sync(ZG_FULL, want, 0);
 		if (base >= nframes) break;
+		prev_base = base;
 		bool mine = lane < want && (u64)base + lane < nframes;
 		u64 t = mine ? (perm ? (u64)perm[base + lane] : (u64)base + lane) : 0;  // work item
 		u64 k = (mine && it.k) ? (u64)it.k[t] : t;                              // its frame
@@ -1136,8 +1141,10 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 		L.b.start = L.b.ptr = archive;
 		L.b.lo = L.b.hi = L.b.consumed = 0;
 		L.sl = L.so = L.sm = 0;
+		u64 mylen = 0;
 		if (mine) {
 			u64 fo = off[k], fl = len[k], ul = ulen[k], oo = out_off[k];
+			mylen = it.k ? it.len[t] : fl;
 			if (fo > archive_len || fl > archive_len - fo) L.status = ZS_E_SRC_SIZE;
 			else if (oo > out_cap || ul > out_cap - oo) L.status = ZS_E_DST_SMALL;
 			else {
@@ -1164,6 +1171,10 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 					}
 				}
 			}
+		}
+		{
+			u32 have = __ballot_sync(ZG_FULL, mine);
+			hint_len = __shfl_sync(ZG_FULL, mylen, have ? 31 - __clz((int)have) : 0);
 		}
 		__syncwarp();
 		// ---- rounds: one block per live frame ----
@@ -1243,7 +1254,7 @@ extern "C" void zg_internal_set_decode_batching(u32 cap_div, u32 min_batch, u32 
 static size_t zd_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len, const u64* ulen,
                         const u64* out_off, u64 count, u8* out, u64 out_cap, u32* status, u64* produced, u32* cksums, ZdItems it) {
 	if (count == 0) return 0;
-	if (count >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
+	if (count >= 0xff000000ull) return ZG_ERR(ZG_error_GENERIC);  // (the queue counter runs past count by up to one batch per warp)
 	u64 batches = (count + 31) / 32;
 	u32 grid = (u32)zg_min<u64>((batches + ZD_WARPS - 1) / ZD_WARPS, (u64)zg_sm_count() * ZD_MIN_CTAS);
 	size_t warps = (size_t)grid * ZD_WARPS;
