@@ -114,9 +114,9 @@ struct ZgZeWork {
 	ZgBuf meta;     // per block: what one kernel hands to the next
 	ZgBuf seqbuf, litbuf, codebuf, stbbuf;  // per chunk staging between (and inside) the kernels
 	ZgBuf bounds;   // first block of every chunk
-	ZgBuf bins, order;  // hand-out order of the blocks: per chunk, largest first
+	ZgBuf bins, order, info;  // hand-out order of the blocks (per chunk, largest first) and the block -> file table
 	void release() {
-		for (ZgBuf* b : {&queue, &meta, &seqbuf, &litbuf, &codebuf, &stbbuf, &bounds, &bins, &order}) b->release();
+		for (ZgBuf* b : {&queue, &meta, &seqbuf, &litbuf, &codebuf, &stbbuf, &bounds, &bins, &order, &info}) b->release();
 	}
 };
 size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,

@@ -1349,6 +1349,12 @@ struct ZeParams {
 	u32 lazy;      // 1: one-step lazy parse (levels >= 3)
 	u32 window;    // reserved
 };
+struct ZeBlk {
+	u32 f;         // file
+	u32 n;         // block bytes
+	u64 j;         // block index inside the file
+	u64 soff;      // offset of the block in the staging blob
+};
 // everything the three kernels need to find a block and its staging
 struct ZeJob {
 	const u8* blob;
@@ -1368,13 +1374,8 @@ struct ZeJob {
 	u64* stbbuf;       // chunk staging: FSE state bits (8 B per 4 input bytes)
 	const u64* bounds; // [nchunks + 1] first block of every chunk
 	const u32* order;  // [nblocks] hand-out order: the blocks of each chunk, largest first (or null: index order)
+	const struct ZeBlk* info;  // [nblocks] block -> (file, size, index, staging offset), or null: binary search (ze_locate)
 	u64 chunk_bytes;
-};
-struct ZeBlk {
-	u32 f;         // file
-	u32 n;         // block bytes
-	u64 j;         // block index inside the file
-	u64 soff;      // offset of the block in the staging blob
 };
 // block -> (unique file, block index): last u with blk_base[u] <= b
 ZG_DEV ZeBlk ze_locate(const ZeJob& J, u64 b) {
@@ -1393,6 +1394,8 @@ ZG_DEV ZeBlk ze_locate(const ZeJob& J, u64 b) {
 	B.soff = J.comp_off[B.f] + boff;
 	return B;
 }
+// the same from the table k_ze_order_scatter filled (one load instead of a 20-step search per block and kernel)
+ZG_DEV ZeBlk ze_block(const ZeJob& J, u64 b) { return J.info ? J.info[b] : ze_locate(J, b); }
 // next block of chunk k from the kernel's queue; false when the chunk is exhausted
 ZG_DEV bool ze_next_block(const ZeJob& J, u32 chunk, u32* queue, u64& b) {
 	u32 t = 0;
@@ -1448,10 +1451,12 @@ __global__ void __launch_bounds__(32) k_ze_order_scan(ZeJob J, u32* bins) {
 		run += __shfl_sync(ZG_FULL, incl, 31);
 	}
 }
-__global__ void __launch_bounds__(256) k_ze_order_scatter(ZeJob J, u32 nchunks, u32* bins, u32* order) {
+__global__ void __launch_bounds__(256) k_ze_order_scatter(ZeJob J, u32 nchunks, u32* bins, u32* order, ZeBlk* info) {
 	u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= J.nblocks) return;
-	order[atomicAdd(&bins[ze_obin_slot(J, ze_locate(J, b), nchunks)], 1u)] = (u32)b;
+	ZeBlk B = ze_locate(J, b);
+	info[b] = B;
+	order[atomicAdd(&bins[ze_obin_slot(J, B, nchunks)], 1u)] = (u32)b;
 }
 
 // K2
@@ -1461,7 +1466,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32, ZE_MIN_CTAS) k_zstd_match_block
 	u32 lane = threadIdx.x & 31;
 	u64 b;
 	while (ze_next_block(J, chunk, queue, b)) {
-		ZeBlk B = ze_locate(J, b);
+		ZeBlk B = ze_block(J, b);
 		u64 rel = B.soff - (u64)chunk * J.chunk_bytes;
 		u64* seq = J.seqbuf + (rel >> 2);
 		u8* lit = J.litbuf + rel;
@@ -1490,7 +1495,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32, ZE_ENT_CTAS) k_zstd_literals(Ze
 		ZeBlkMeta m = J.meta[b];
 		u32 litsec = 0;
 		if (m.nseq != ZE_RAW) {
-			ZeBlk B = ze_locate(J, b);
+			ZeBlk B = ze_block(J, b);
 			u64 rel = B.soff - (u64)chunk * J.chunk_bytes;
 			litsec = ze_literals_section(W, J.litbuf + rel, m.nlit, J.comp + B.soff, B.n - 1);
 		}
@@ -1515,7 +1520,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32, ZE_ENT_CTAS) k_zstd_sequences(Z
 	u64 b;
 	while (ze_next_block(J, chunk, queue, b)) {
 		ZeBlkMeta m = J.meta[b];
-		ZeBlk B = ze_locate(J, b);
+		ZeBlk B = ze_block(J, b);
 		u32 csize = 0;
 		if (m.nseq != ZE_RAW && m.litsec) {
 			u64 rel = B.soff - (u64)chunk * J.chunk_bytes;
@@ -1559,7 +1564,8 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	    w.codebuf.reserve(span) || w.stbbuf.reserve(span * 2) || w.bounds.reserve(((size_t)nchunks + 1) * 8))
 		return ZG_ERR(ZG_error_memory_allocation);
 	const bool sorted = nblocks > 8 && nblocks < 0xffffffffull;
-	if (sorted && (w.bins.reserve((size_t)nchunks * ZE_OBINS * 4) || w.order.reserve(nblocks * 4))) return ZG_ERR(ZG_error_memory_allocation);
+	if (sorted && (w.bins.reserve((size_t)nchunks * ZE_OBINS * 4) || w.order.reserve(nblocks * 4) || w.info.reserve(nblocks * sizeof(ZeBlk))))
+		return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.queue.p, 0, qbytes, s);
 	ZeParams prm;
 	prm.lazy = level >= 3 ? 1 : 0;
@@ -1582,6 +1588,7 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	J.stbbuf = w.stbbuf.as<u64>();
 	J.bounds = w.bounds.as<u64>();
 	J.order = nullptr;
+	J.info = nullptr;
 	J.chunk_bytes = chunk_bytes;
 	size_t smem_m = sizeof(ZeMatchWarp) * ZE_WARPS;
 	size_t smem_l = sizeof(ZeWarp) * ZE_WARPS;
@@ -1602,9 +1609,10 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 		u32 g = (u32)((nblocks + 255) / 256);
 		ZG_LAUNCH(k_ze_order_count, g, 256, 0, s, J, nchunks, w.bins.as<u32>());
 		ZG_LAUNCH(k_ze_order_scan, nchunks, 32, 0, s, J, w.bins.as<u32>());
-		ZG_LAUNCH(k_ze_order_scatter, g, 256, 0, s, J, nchunks, w.bins.as<u32>(), w.order.as<u32>());
+		ZG_LAUNCH(k_ze_order_scatter, g, 256, 0, s, J, nchunks, w.bins.as<u32>(), w.order.as<u32>(), w.info.as<ZeBlk>());
 		g_zg_launches += 3;
 		J.order = w.order.as<u32>();
+		J.info = w.info.as<ZeBlk>();
 	}
 	u32* q = w.queue.as<u32>();
 	for (u32 k = 0; k < nchunks; k++) {
