@@ -788,9 +788,9 @@ ZG_DEV void zd_lane_overlap(u8* d, u32 off, u32 ml) {
 
 // Phase C: execute `cnt` (<= 32) sequences, one per lane.  Output and literal positions come from
 // warp scans.  All literal runs are independent and copied first, lane-parallel.  Matches then go in
-// waves: a match is ready once every earlier match of the row that starts before its source's end
-// has been written (match starts grow with the lane, so that set is a prefix of the lanes); all ready
-// matches of a wave copy lane-parallel.  A row of n sequences takes (dependency depth) waves, not n
+// waves: a match is ready once every earlier match of the row whose output its source overlaps has been
+// written (match starts and ends grow with the lane, so that set is a range of lanes, found by two binary
+// searches over shuffles); all ready matches of a wave copy lane-parallel.  A row of n sequences takes (dependency depth) waves, not n
 // steps, and every wave is a few 16-byte round trips.
 ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, u8* out, u64& o_io, u64 base, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte,
                        u32 regen, u32& lpos_io) {
@@ -835,7 +835,19 @@ ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, u8* out, u64& o_io, u64 base, u64 c
 		if (v < send) nlow += (u32)s;
 	}
 	nlow = zg_min<u32>(nlow, lane);
-	u32 need = (1u << nlow) - 1u;
+	// ... and of those, not the ones whose match ends at or before my source begins (match ends grow with the
+	// lane too): what is left is exactly the lanes whose output my source overlaps.  Waiting for the whole prefix
+	// instead would push every later match behind the deepest chain seen so far.
+	i32 re = act ? (i32)(rstart + ml) : 0x7fffffff;
+	i32 sbeg = (i32)rstart - (i32)of;
+	u32 nlo = 0;
+	ZG_UNROLL
+	for (int s = 16; s >= 1; s >>= 1) {
+		i32 v = __shfl_sync(ZG_FULL, re, (int)(nlo + (u32)s - 1u));
+		if (v <= sbeg) nlo += (u32)s;
+	}
+	nlo = zg_min<u32>(nlo, nlow);
+	u32 need = ((1u << nlow) - 1u) & ~((1u << nlo) - 1u);
 	u32 pending = __ballot_sync(ZG_FULL, act && ml > 0);
 	__syncwarp();  // the literals are written
 	while (pending) {
