@@ -37,6 +37,17 @@ def test_blake3_big_file_path(emu):
         assert g == blake3.blake3(f).digest(), len(f)
 
 
+def test_xxh64_large_inputs_whole_warp_path(emu):
+    """Large inputs through the one-warp-per-input path (1 KiB chunks through shared memory)."""
+    import xxhash
+
+    files = [_data((1 << 20) + 13), _data(1 << 20, 1), _data((1 << 20) - 1, 2), _data(3 * (1 << 20) + 1024 + 31, 3), _data(100, 4)]
+    for shift in (0, 3):
+        got = xxh64_batch(emu, files, shift=shift)
+        for f, g in zip(files, got):
+            assert g == xxhash.xxh64(f, seed=0).intdigest(), len(f)
+
+
 @pytest.mark.parametrize("shift", [0, 1, 8])
 def test_xxh64_sizes(emu, shift):
     import xxhash

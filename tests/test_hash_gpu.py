@@ -46,3 +46,9 @@ def test_xxh64_sizes(gpu, shift):
     got = xxh64_batch(gpu, files, shift=shift)
     for f, g in zip(files, got):
         assert g == xxhash.xxh64(f, seed=0).intdigest() == ref_path.c_xxh64(f), len(f)
+
+
+def test_xxh64_large_inputs_whole_warp_path(gpu):
+    from tests import test_hash_emu as cases
+
+    cases.test_xxh64_large_inputs_whole_warp_path(gpu)
