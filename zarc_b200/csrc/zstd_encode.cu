@@ -1232,54 +1232,118 @@ ZG_DEV u32 ze_sequences_tables(ZeWarp* W, ZePredef* P, const u64* seq, u32* code
 	return (u32)(p - dst);
 }
 
-// The three FSE state chains of one block (last sequence first, libzstd's ZSTD_encodeSequences
-// order) are independent of each other: lanes 0,1,2 walk one each over the tables in shared memory,
-// leaving per sequence the bits the chain emits as a 16-bit field (value | nbBits << 12) of a 64-bit
-// word: LL | ML << 16 | OF << 32.  Four steps per trip: the symbol codes and their table rows are
-// fetched up front, only the state look-ups are serial.  All lanes call; fills M.fin.
+// The three FSE state chains of one block (last sequence first, libzstd's ZSTD_encodeSequences order), leaving
+// per sequence the bits each chain emits as a 16-bit field (value | nbBits << 12) of a 64-bit word:
+// LL | ML << 16 | OF << 32.
+// A chain is serial -- the state after a step depends on the state before it -- but it forgets: encoding a symbol
+// of normalized count c keeps only which of c sub-ranges the old state was in, so two walks over the same symbols
+// from different states merge after a few steps and stay merged; across a symbol of count 1 (a single state:
+// nbBits = tableLog, (state >> tableLog) == 1, next state st[1 + deltaFindState]) they merge at once.  So each
+// chain is cut into ZE_CHAIN_LANES ranges of steps, one lane each.  A lane looks upwards from its range for the
+// nearest count-1 symbol (or the chain's start) within ZE_CHAIN_WARM steps; from there the state is exact.
+// Failing that it starts ZE_CHAIN_WARM steps up from a guessed state.  It walks down to its range without output
+// and then produces its range.  Afterwards the ranges are checked in chain order: a lane that started from a guess
+// must have entered its range in the state the lane above left off in; if not (rare) it walks its range again
+// from the right state.  The fields are bit for bit those of the serial walk.  All lanes call; fills M.fin.
+#define ZE_CHAIN_LANES 10u
+#define ZE_CHAIN_WARM 96u
+struct ZeChainRun {
+	const u32* codes;
+	const u16* st;
+	const ZeSymTT* tt;
+	u16* out;
+	u32 sh;
+};
+// steps from-1 .. to (descending) from `state`; four per trip, the codes and their table rows fetched up front so
+// that only the state look-ups are serial
+ZG_DEV u32 ze_chain_walk(const ZeChainRun& R, u32 state, u32 from, u32 to, bool emit) {
+	u32 i = from;
+	ZG_UNROLL1
+	while (i > to) {
+		u32 m = zg_min<u32>(4u, i - to);
+		ZeSymTT r[4];
+		ZG_UNROLL
+		for (u32 k = 0; k < 4; k++)
+			if (k < m) r[k] = R.tt[(R.codes[i - 1 - k] >> R.sh) & 0xff];
+		ZG_UNROLL
+		for (u32 k = 0; k < 4; k++) {
+			if (k < m) {
+				u32 nb = (state + r[k].dnb) >> 16;
+				if (emit) R.out[4 * (i - 1 - k)] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
+				state = R.st[(state >> nb) + r[k].dfs];
+			}
+		}
+		i -= m;
+	}
+	return state;
+}
 ZG_DEV void ze_sequences_chains(ZeWarp* W, const u32* codes, u16* stb16, ZeBlkMeta& M) {
 	ZeEnt& e = W->e;
 	u32 lane = zg_lane();
 	u32 nseq = M.nseq;
-	if (lane < 3) {
-		u32 sh = 8 * lane;  // codes = ll | ml << 8 | of << 16; table index 0 LL, 1 ML, 2 OF
-		const u16* st = e.st[lane];
-		const ZeSymTT* tt = e.tt[lane];
-		u32 log = (M.logs >> sh) & 0xff;
-		u16* out = stb16 + lane;  // stride 4
-		ZeCT ct{e.st[lane], e.tt[lane], log};
-		u32 state = ze_fse_init_state(ct, (codes[nseq - 1] >> sh) & 0xff);
-		out[4 * (nseq - 1)] = 0;
-		u32 i = nseq - 1;
-		u32 c4[4] = {0, 0, 0, 0};
-		if (i >= 4) {
-			ZG_UNROLL
-			for (int k = 0; k < 4; k++) c4[k] = codes[i - 1 - k];
-		}
-		while (i >= 4) {
-			ZeSymTT r[4];
-			ZG_UNROLL
-			for (int k = 0; k < 4; k++) r[k] = tt[(c4[k] >> sh) & 0xff];
-			if (i >= 8) {  // the next trip's codes are on their way while this trip's states resolve
-				ZG_UNROLL
-				for (int k = 0; k < 4; k++) c4[k] = codes[i - 5 - k];
+	u32 S = nseq - 1;  // steps: step j encodes codes[j], j = S-1 .. 0; the chain starts from codes[nseq - 1]
+	u32 t = lane / ZE_CHAIN_LANES, sub = lane % ZE_CHAIN_LANES;
+	u32* xch = W->hist;  // per lane: state on entering the range | state on leaving it << 16 (the literal histogram is not in use here)
+	bool live = false, exact = true;
+	u32 hi = 0, lo = 0, s_in = 0, s_out = 0, log = 0;
+	ZeChainRun R{codes, nullptr, nullptr, nullptr, 0};
+	if (t < 3) {
+		R.sh = 8 * t;  // codes = ll | ml << 8 | of << 16; table index 0 LL, 1 ML, 2 OF
+		R.st = e.st[t];
+		R.tt = e.tt[t];
+		R.out = stb16 + t;  // stride 4
+		log = (M.logs >> R.sh) & 0xff;
+		u32 reset_dnb = (log << 16) - (1u << log);  // deltaNbBits of a symbol with a single state
+		u32 len = (S + ZE_CHAIN_LANES - 1) / ZE_CHAIN_LANES;
+		hi = S - zg_min<u32>(S, sub * len);
+		lo = S - zg_min<u32>(S, (sub + 1) * len);
+		if (sub == 0) R.out[4 * S] = 0;
+		live = hi > lo || (sub == 0 && S == 0);
+		if (live) {
+			ZeCT ct{e.st[t], e.tt[t], log};
+			u32 top = zg_min<u32>(S, hi + ZE_CHAIN_WARM);
+			u32 from = hi, state = 0;
+			bool found = false;
+			ZG_UNROLL1
+			while (from < top) {
+				ZeSymTT r = R.tt[(codes[from] >> R.sh) & 0xff];
+				if (r.dnb == reset_dnb) {
+					state = R.st[1 + r.dfs];
+					found = true;
+					break;
+				}
+				from++;
 			}
-			ZG_UNROLL
-			for (int k = 0; k < 4; k++) {
-				u32 nb = (state + r[k].dnb) >> 16;
-				out[4 * (i - 1 - k)] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-				state = st[(state >> nb) + r[k].dfs];
+			if (!found) {
+				// the chain's start if it is within reach, else a guess: walk as if the chain started at `top`
+				state = ze_fse_init_state(ct, (codes[top] >> R.sh) & 0xff);
+				from = top;
+				exact = top == S;
 			}
-			i -= 4;
+			s_in = ze_chain_walk(R, state, from, hi, false);
+			s_out = ze_chain_walk(R, s_in, hi, lo, true);
+			xch[lane] = s_in | (s_out << 16);
 		}
-		while (i-- > 0) {
-			ZeSymTT r = tt[(codes[i] >> sh) & 0xff];
-			u32 nb = (state + r.dnb) >> 16;
-			out[4 * i] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
-			state = st[(state >> nb) + r.dfs];
-		}
-		W->misc[8 + lane] = state & ((1u << log) - 1u);
 	}
+	__syncwarp();
+	// in chain order: a guessed start must have merged with the true chain before the range began
+	ZG_UNROLL1
+	for (u32 k = 1; k < ZE_CHAIN_LANES; k++) {
+		bool redo = false;
+		u32 s_true = 0;
+		if (live && sub == k && !exact) {
+			s_true = xch[lane - 1] >> 16;  // the lane above holds the range above (its final state, corrected if need be)
+			redo = s_true != s_in;
+		}
+		if (__any_sync(ZG_FULL, redo)) {
+			if (redo) {
+				s_out = ze_chain_walk(R, s_true, hi, lo, true);
+				xch[lane] = s_true | (s_out << 16);
+			}
+		}
+		__syncwarp();
+	}
+	if (live && lo == 0) W->misc[8 + t] = s_out & ((1u << log) - 1u);
 	__syncwarp();
 	M.fin[0] = W->misc[8];
 	M.fin[1] = W->misc[9];
