@@ -309,10 +309,10 @@ def main():
     if os.environ.get("ZG_DECODE_BATCHING"):  # tuning aid: "cap_div,min_batch_bytes,floor_bytes"
         a, b, c3 = os.environ["ZG_DECODE_BATCHING"].split(",")
         lib.dll.zg_internal_set_decode_batching(C.c_uint32(int(a)), C.c_uint32(int(b)), C.c_uint32(int(c3)))
-    if os.environ.get("ZG_PACK_SLICE_MB"):  # tuning aid: host-API slice size, pack only
-        lib.dll.zg_internal_set_pack_slice_bytes(C.c_uint64(int(os.environ["ZG_PACK_SLICE_MB"]) << 20))
     if os.environ.get("ZG_SLICE_MB"):  # tuning aid: host-API slice size
         lib.dll.zg_internal_set_slice_bytes(C.c_uint64(int(os.environ["ZG_SLICE_MB"]) << 20))
+    if os.environ.get("ZG_PACK_SLICE_MB"):  # tuning aid: host-API slice size, pack only
+        lib.dll.zg_internal_set_pack_slice_bytes(C.c_uint64(int(os.environ["ZG_PACK_SLICE_MB"]) << 20))
     lib.zg_profile_enable(1)
     launches0 = lib.zg_kernel_launch_count()
     sync_all()
