@@ -10,7 +10,7 @@
 #include <vector>
 #include <string.h>
 
-uint64_t g_zg_launches = 0;
+std::atomic<uint64_t> g_zg_launches{0};
 // Slices of the host-buffer API.  Unpack wants ~100 K frames in flight per launch (1 GiB of C2-shaped output); the
 // encoder's kernels keep their efficiency on less, and smaller pack slices expose less of the first upload.
 uint64_t g_zg_slice_bytes = 1024ull << 20;
@@ -195,7 +195,7 @@ const char* zg_build_info(void) {
 	return "sm_100a";
 #endif
 }
-uint64_t zg_kernel_launch_count(void) { return g_zg_launches; }
+uint64_t zg_kernel_launch_count(void) { return g_zg_launches.load(); }
 void* zg_alloc_pinned(size_t n) {
 	void* p = nullptr;
 	if (dev_count() <= 0 || cudaMallocHost(&p, n ? n : 1) != cudaSuccess) return nullptr;

@@ -1,12 +1,13 @@
 // Internal declarations shared by the kernels' launchers and the C ABI.
 #pragma once
+#include <atomic>
 #include "simt.h"
 #include "../../include/zarcgpu.h"
 
 #define ZG_ERR(code) ((size_t)0 - (size_t)(code))
 
 extern uint64_t g_zg_slice_bytes, g_zg_pack_slice_bytes;  // host-buffer API: bytes per pipelined slice, unpack / pack (tests shrink them)
-extern uint64_t g_zg_launches;  // kernels launched by this library (bench.py's gpu_launches)
+extern std::atomic<uint64_t> g_zg_launches;  // kernels launched by this library (bench.py's gpu_launches)
 #define ZG_COUNT_LAUNCH() (++g_zg_launches)
 
 // grow-only device buffer

@@ -1050,10 +1050,6 @@ k_zd_join(const u8* __restrict__ archive, const u64* __restrict__ off, const u64
 	for (u64 i = lane; i < nb; i += 32) {
 		u64 share = i + 1 < nb ? (u64)ZS_BLOCK_MAX : ul - (nb - 1) * ZS_BLOCK_MAX;
 		good = good && it_status[first + i] == ZS_OK && it_prod[first + i] == share;
-#ifdef ZG_EMU
-		if (getenv("ZG_DBG_JOIN") && !(it_status[first + i] == ZS_OK && it_prod[first + i] == share))
-			fprintf(stderr, "join: frame %llu block %llu status %u prod %llu share %llu\n", (unsigned long long)k, (unsigned long long)i, it_status[first + i], (unsigned long long)it_prod[first + i], (unsigned long long)share);
-#endif
 	}
 	good = __all_sync(ZG_FULL, good);
 	if (lane) return;
