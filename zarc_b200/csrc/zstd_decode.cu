@@ -173,7 +173,7 @@ ZG_DEV void zd_warp_match(u8* d, u32 off, u32 ml) {
 // ---------------------------------------------------------------------------------------------
 // Huffman tree description -> W->weights[0..nw) (the last weight is implied).  Returns bytes
 // consumed (0 on error).  All lanes call.
-ZG_DEV u32 zd_read_huf_weights(ZdWarp* W, const u8* src, u32 n, u32* nw_out) {
+ZG_DEV_NOINLINE u32 zd_read_huf_weights(ZdWarp* W, const u8* src, u32 n, u32* nw_out) {
 	u32 lane = zg_lane();
 	if (n < 1) return 0;
 	u32 h = src[0];
@@ -246,7 +246,7 @@ ZG_DEV u32 zd_read_huf_weights(ZdWarp* W, const u8* src, u32 n, u32* nw_out) {
 }
 
 // W->weights[0..nw) -> W->huf.  Returns maxbits (0 on error).  All lanes call.
-ZG_DEV u32 zd_build_huf(ZdWarp* W, u32 nw) {
+ZG_DEV_NOINLINE u32 zd_build_huf(ZdWarp* W, u32 nw) {
 	u32 lane = zg_lane();
 	// weights -> last weight, ranks, per-symbol start index (serial, <= 256 symbols)
 	if (lane == 0) {
@@ -340,7 +340,7 @@ ZG_DEV bool zd_huf_stream(const u16* huf, u32 maxbits, const u8* src, u32 n, u8*
 
 // sequence table for one of LL/OF/ML into the lane's global slot `slot`.  All lanes call (uniform).
 // Returns false on error; advances p.  `flags`: def_flag is set when the predefined table is in use.
-ZG_DEV bool zd_seq_table(ZdWarp* W, u32* slot, u32& log, u32& flags, u32 ok_flag, u32 def_flag, u32 mode, const u8*& p, const u8* end,
+ZG_DEV_NOINLINE bool zd_seq_table(ZdWarp* W, u32* slot, u32& log, u32& flags, u32 ok_flag, u32 def_flag, u32 mode, const u8*& p, const u8* end,
                          u32 maxlog, u32 maxsym, u32 def_log) {
 	u32 lane = zg_lane();
 	if (mode == 0) {
@@ -498,7 +498,7 @@ ZG_DEV bool zd_lit_header(const u8* src, u32 n, ZdLitHdr& h) {
 
 // The block's literals (uniform in the warp): Raw -> pointer into the block, RLE -> the byte,
 // Huffman -> decoded into litbuf.  Returns a ZS_E_* code.
-ZG_DEV u32 zd_literals(ZdWarp* W, u32& flags, const u8* src, const ZdLitHdr& h, bool last, u8* litbuf, u8* hufsave, const u8*& lit,
+ZG_DEV_NOINLINE u32 zd_literals(ZdWarp* W, u32& flags, const u8* src, const ZdLitHdr& h, bool last, u8* litbuf, u8* hufsave, const u8*& lit,
                        bool& lit_rle, u32& rle_byte) {
 	u32 lane = zg_lane();
 	lit_rle = false;
