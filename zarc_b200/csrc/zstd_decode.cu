@@ -121,7 +121,7 @@ ZG_DEV ZdLane zd_bcast(const ZdLane& L, int f) {
 
 // ---------------------------------------------------------------------------------------------
 // warp-cooperative copies
-ZG_DEV void zg_warp_copy(u8* dst, const u8* src, u32 n) {
+ZG_DEV_NOINLINE void zg_warp_copy(u8* dst, const u8* src, u32 n) {
 	u32 lane = zg_lane();
 	if (n < 128) {
 		for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
@@ -151,7 +151,7 @@ ZG_DEV void zg_warp_copy(u8* dst, const u8* src, u32 n) {
 	}
 	for (u32 i = (nvec << 4) + lane; i < n; i += 32) dst[i] = src[i];
 }
-ZG_DEV void zg_warp_fill(u8* dst, u32 byte, u32 n) {
+ZG_DEV_NOINLINE void zg_warp_fill(u8* dst, u32 byte, u32 n) {
 	for (u32 i = zg_lane(); i < n; i += 32) dst[i] = (u8)byte;
 }
 // match copy inside the frame output: d[i] = d[i - off], forward semantics (overlap allowed)
@@ -320,7 +320,7 @@ ZG_DEV_NOINLINE u32 zd_build_huf(ZdWarp* W, u32 nw) {
 }
 
 // one Huffman stream, single thread
-ZG_DEV bool zd_huf_stream(const u16* huf, u32 maxbits, const u8* src, u32 n, u8* dst, u32 count) {
+ZG_DEV_NOINLINE bool zd_huf_stream(const u16* huf, u32 maxbits, const u8* src, u32 n, u8* dst, u32 count) {
 	ZsBack b;
 	if (!zs_back_init(b, src, n)) return false;
 	u32 i = 0;
