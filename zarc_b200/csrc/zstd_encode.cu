@@ -565,7 +565,13 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 // total code bits of lit[0..m)
 ZG_DEV_NOINLINE u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
 	u32 bits = 0;
-	for (u32 i = zg_lane(); i < m; i += 32) bits += e.hcode[lit[i]] >> 11;
+	u32 lane = zg_lane();
+	u32 b_next = lane < m ? lit[lane] : 0u;  // one trip ahead
+	for (u32 i = lane; i < m; i += 32) {
+		u32 b = b_next;
+		b_next = i + 32 < m ? lit[i + 32] : 0u;
+		bits += e.hcode[b] >> 11;
+	}
 	return zg_warp_sum(bits);
 }
 
@@ -1048,10 +1054,12 @@ ZG_DEV u32 ze_literals_section(ZeWarp* W, const u8* lit, u32 nlit, u8* dst, u32 
 	u8* p = dst;
 	for (u32 i = lane; i < 256; i += 32) W->hist[i] = 0;
 	__syncwarp();
+	u32 w_next = 4 * lane + 4 <= nlit ? *(const u32*)(lit + 4 * lane) : 0u;  // the next trip's word is on its way during this trip
 	for (u32 i0 = 0; i0 < nlit; i0 += 128) {  // 4 literals per lane per trip
 		u32 i = i0 + 4 * lane;
+		u32 w = w_next;
+		w_next = i + 132 <= nlit ? *(const u32*)(lit + i + 128) : 0u;  // the literal buffer of a block is 16-byte aligned
 		if (i + 4 <= nlit) {
-			u32 w = *(const u32*)(lit + i);  // the literal buffer of a block is 16-byte aligned
 			atomicAdd(&W->hist[w & 0xff], 1u);
 			atomicAdd(&W->hist[(w >> 8) & 0xff], 1u);
 			atomicAdd(&W->hist[(w >> 16) & 0xff], 1u);
@@ -1199,8 +1207,10 @@ ZG_DEV u32 ze_sequences_tables(ZeWarp* W, ZePredef* P, const u64* seq, u32* code
 	for (u32 i = lane; i < 3 * 64; i += 32) (&e.hist3[0][0])[i] = 0;
 	__syncwarp();
 	u32 mx_ll = 0, mx_ml = 0, mx_of = 0;
+	u64 q_next = lane < nseq ? seq[lane] : 0;  // the records of the next trip are on their way while this one is coded
 	for (u32 i = lane; i < nseq; i += 32) {
-		u64 q = seq[i];
+		u64 q = q_next;
+		q_next = i + 32 < nseq ? seq[i + 32] : 0;
 		u32 lc = ze_ll_code(ZE_SEQ_LL(q)), mc = ze_ml_code(ZE_SEQ_ML(q) - 3), oc = zs_highbit(ZE_SEQ_OF(q));
 		codes[i] = lc | (mc << 8) | (oc << 16);
 		atomicAdd(&e.hist3[0][lc], 1u);
@@ -1361,14 +1371,28 @@ ZG_DEV u32 ze_sequences_pack(ZeWarp* W, const u64* seq, const u32* codes, const 
 	u32 logs[3] = {M.logs & 0xff, (M.logs >> 8) & 0xff, M.logs >> 16};
 	ZePack pk;
 	ze_pack_init(pk, e.window, dst, cap);
+	// (the three loads of the next trip are issued before this trip's fields are assembled and packed)
+	u32 c_next = 0;
+	u64 sb_next = 0, q_next = 0;
+	if (lane < nseq) {
+		u32 i = nseq - 1 - lane;
+		c_next = codes[i];
+		sb_next = stb[i];
+		q_next = seq[i];
+	}
 	for (u32 hi = nseq; hi > 0; hi -= zg_min<u32>(hi, 32u)) {
 		u64 lo64 = 0;
 		u32 hi32 = 0, nb = 0;
+		u32 c = c_next;
+		u64 sb = sb_next, q = q_next;
+		if (hi > 32 && lane < hi - 32) {
+			u32 i = hi - 33 - lane;
+			c_next = codes[i];
+			sb_next = stb[i];
+			q_next = seq[i];
+		}
 		if (lane < hi) {
-			u32 i = hi - 1 - lane;
-			u32 c = codes[i];
 			u32 lc = c & 0xff, mc = (c >> 8) & 0xff, oc = c >> 16;
-			u64 sb = stb[i];
 			u32 a = (u32)(sb >> 32) & 0xffff, b = (u32)(sb >> 16) & 0xffff, d = (u32)sb & 0xffff;
 			lo64 = a & 0xfff;
 			nb = a >> 12;
@@ -1376,7 +1400,6 @@ ZG_DEV u32 ze_sequences_pack(ZeWarp* W, const u64* seq, const u32* codes, const 
 			nb += b >> 12;
 			lo64 |= (u64)(d & 0xfff) << nb;
 			nb += d >> 12;
-			u64 q = seq[i];
 			lo64 |= (u64)(ZE_SEQ_LL(q) - ZS_LL_BASE[lc]) << nb;
 			nb += ZS_LL_BITS[lc];
 			lo64 |= (u64)(ZE_SEQ_ML(q) - ZS_ML_BASE[mc]) << nb;
