@@ -51,6 +51,39 @@ def test_compress2_flags_and_errors(emu):
     emu.zg_cctx_free(c)
 
 
+def few_sequence_inputs():
+    """Blocks with 1, 2, 3 ... a few dozen sequences (the FSE state chains are cut into ten ranges per chain: every
+    count around that has to come out right), blocks made of one repeated phrase (RLE sequence tables), and blocks whose
+    sequence codes are all distinct (count-1 symbols everywhere)."""
+    rng = np.random.default_rng(2024)
+    phrase = rand(37, 3)
+    out = []
+    for k in range(1, 48):  # k phrases re-used once each, separated by fresh bytes: about k sequences
+        parts = []
+        for j in range(k):
+            parts.append(rand(int(rng.integers(9, 30)), 100 * k + j))
+            parts.append(phrase[: int(rng.integers(8, 37))])
+        out.append(phrase + b"".join(parts))
+    out.append((phrase + rand(5, 9)) * 300)                      # identical sequences: RLE tables
+    out.append(b"".join(rand(6 + j % 40, j) + phrase[: 5 + j % 30] for j in range(400)))  # varied lengths and offsets
+    out.append(text(3000, 77) + bytes(4000) + text(3000, 77))    # long match, long zero run
+    return out
+
+
+@pytest.mark.parametrize("level", [1, 3])
+def test_few_sequences_and_chain_ranges(emu, level):
+    datas = few_sequence_inputs()
+    cctx = emu.zg_cctx_create()
+    emu.check(emu.zg_cctx_init(cctx, level))
+    emu.check(emu.zg_cctx_set_parameter(cctx, 201, 1))
+    emu.check(emu.zg_cctx_reset_archive(cctx, 12))
+    r = pack_batch(emu, cctx, datas)
+    emu.zg_cctx_free(cctx)
+    assert r["rc"] == 0
+    for d, o, l in zip(datas, r["off"], r["len"]):
+        _check_frame(emu, d, bytes(r["frames"][o - 12 : o - 12 + l]))
+
+
 def test_ratio_vs_reference_small_corpus(emu):
     from zarc_b200 import corpus
 

@@ -25,6 +25,11 @@ def test_compress2_flags_and_errors(gpu):
     cases.test_compress2_flags_and_errors(gpu)
 
 
+@pytest.mark.parametrize("level", [1, 3])
+def test_few_sequences_and_chain_ranges(gpu, level):
+    cases.test_few_sequences_and_chain_ranges(gpu, level)
+
+
 def test_ratio_vs_reference_small_corpus(gpu):
     cases.test_ratio_vs_reference_small_corpus(gpu)
 
