@@ -331,14 +331,25 @@ ZG_DEV_NOINLINE bool zd_huf_stream(const u16* huf, u32 maxbits, const u8* src, u
 	ZsBack b;
 	if (!zs_back_init(b, src, n)) return false;
 	u32 i = 0;
+	const u32 sh = 32u - maxbits;
 	while (i < count) {
 		zs_back_reload(b);
 		u32 m = zg_min<u32>(count - i, 5u);  // 5 x 11 bits <= 57
+		// the unread bits left-aligned in ah:al; every symbol then costs one shift for the index and a two-word
+		// shift for the bits it used (bits before the start of the stream shift in as zeros)
+		u32 c = b.consumed;
+		u32 ah = c < 32 ? __funnelshift_l(b.lo, b.hi, c) : (c < 64 ? b.lo << (c & 31u) : 0u);
+		u32 al = c < 32 ? b.lo << c : 0u;
+		u32 used = 0;
 		for (u32 k = 0; k < m; k++) {
-			u32 e = huf[zs_back_look(b, maxbits)];
+			u32 e = huf[ah >> sh];
 			dst[i + k] = (u8)e;
-			zs_back_skip(b, e >> 8);
+			u32 nb = e >> 8;
+			ah = __funnelshift_l(al, ah, nb);
+			al <<= nb;
+			used += nb;
 		}
+		b.consumed = c + used;
 		i += m;
 	}
 	zs_back_reload(b);
