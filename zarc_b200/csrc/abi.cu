@@ -60,6 +60,15 @@ int zg_sm_count() {
 	do {               \
 		if ((expr) != cudaSuccess) return ZG_ERR(ZG_error_memory_allocation); \
 	} while (0)
+// no exception crosses the C boundary: host allocations sized by caller- or archive-controlled numbers fail as error codes
+#define ZG_GUARD(expr)                                    \
+	try {                                                 \
+		return (expr);                                    \
+	} catch (const std::bad_alloc&) {                     \
+		return ZG_ERR(ZG_error_memory_allocation);        \
+	} catch (...) {                                       \
+		return ZG_ERR(ZG_error_GENERIC);                  \
+	}
 
 // ---------------------------------------------------------------------------------------------
 // host-side frame boundary walk: frame header + 3-byte block headers only (no content decoding).
@@ -91,6 +100,9 @@ static size_t host_frame_size(const uint8_t* p, size_t n, uint64_t* bound, bool*
 	}
 	if (checksum) ip += 4;
 	if (n < ip) return 0;
+	// a frame cannot regenerate more than 128 KiB per block: a Frame_Content_Size beyond that is a lie (and would
+	// otherwise size host and device buffers from an untrusted 64-bit field)
+	if (fcs_len && fcs > blocks * 131072ull) return ZG_ERR(ZG_error_corruption_detected);
 	if (bound) *bound = fcs_len ? fcs : blocks * 131072ull;
 	if (has_fcs) *has_fcs = fcs_len != 0;
 	return ip;
@@ -103,7 +115,7 @@ struct zg_dctx {
 	int verify_checksum = 1;
 	ZgZdWork zd;
 	ZgB3Work b3;
-	ZgBuf status, produced, cksums, got_digests, first, tiles, packed_off;
+	ZgBuf status, produced, cksums, got_digests, first, tiles, packed_off, vspan;
 	// host-API staging: two stages, so that the copies of one slice overlap the kernels of another
 	struct Stage {
 		ZgBuf d_archive, d_meta, d_out, d_digests, d_ok;
@@ -143,7 +155,11 @@ static size_t unpack_core(zg_dctx* d, const u8* archive, u64 archive_len, u64 n,
 	ZG_TRY(zg_unpack_finalize_run(s, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum));
 	if (digests && ok) {
 		ZG_ALLOC(d->got_digests.reserve(n * 32));
-		ZG_TRY(zg_blake3_run(s, d->b3, out, out_off, ulen, n, d->got_digests.as<u8>()));
+		ZG_ALLOC(d->vspan.reserve(n * 16));
+		// only frames that decoded are hashed: a rejected frame's output span may lie outside `out`
+		u64* voff = d->vspan.as<u64>();
+		ZG_TRY(zg_verify_spans_run(s, st, out_off, ulen, out_cap, n, voff, voff + n));
+		ZG_TRY(zg_blake3_run(s, d->b3, out, voff, voff + n, n, d->got_digests.as<u8>()));
 		ZG_TRY(zg_digest_compare_run(s, d->got_digests.as<u8>(), digests, st, ok, n));
 	}
 	ZG_TRY(zg_first_error_run(s, st, n, d->first.as<u64>()));
@@ -309,11 +325,14 @@ struct zg_hasher {
 	std::vector<uint8_t> acc;
 };
 zg_hasher* zg_hasher_new(void) { return new (std::nothrow) zg_hasher(); }
-size_t zg_hasher_update(zg_hasher* h, const void* data, size_t len) {
-	if (!h) return ZG_ERR(ZG_error_GENERIC);
+static size_t hasher_update_impl(zg_hasher* h, const void* data, size_t len) {
 	const uint8_t* p = (const uint8_t*)data;
 	h->acc.insert(h->acc.end(), p, p + len);
 	return 0;
+}
+size_t zg_hasher_update(zg_hasher* h, const void* data, size_t len) {
+	if (!h || (!data && len)) return ZG_ERR(ZG_error_GENERIC);
+	ZG_GUARD(hasher_update_impl(h, data, len));
 }
 size_t zg_hasher_finalize(zg_hasher* h, uint8_t out[32]) {
 	if (!h) return ZG_ERR(ZG_error_GENERIC);
@@ -339,7 +358,7 @@ void zg_dctx_free(zg_dctx* d) {
 	cudaStreamSynchronize(d->stream);
 	d->zd.release();
 	zg_b3work_free(d->b3);
-	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->d_archive,
+	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->vspan, &d->d_archive,
 	                 &d->d_meta, &d->d_out})
 		b->release();
 	for (auto& st : d->hstage) {
@@ -385,9 +404,9 @@ size_t zg_unpack_batch_dev(zg_dctx* d, const uint8_t* archive, uint64_t archive_
 
 // Host-buffer unpack, sliced and double-buffered like pack_host (abi_pack.cu): the archive bytes of
 // slice k+1 go up and the restored files of slice k-1 come down while slice k decodes.
-size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len, uint64_t n, const uint64_t* off,
-                       const uint64_t* len, const uint64_t* ulen, const uint8_t* digests, uint8_t* out, uint64_t out_cap,
-                       const uint64_t* out_off, uint8_t* ok, uint32_t* status) {
+static size_t unpack_batch_impl(zg_dctx* d, const uint8_t* archive, uint64_t archive_len, uint64_t n, const uint64_t* off,
+                                const uint64_t* len, const uint64_t* ulen, const uint8_t* digests, uint8_t* out, uint64_t out_cap,
+                                const uint64_t* out_off, uint8_t* ok, uint32_t* status) {
 	ZG_NEED_DEVICE();
 	if (!d) return ZG_ERR(ZG_error_GENERIC);
 	if (n == 0) return 0;
@@ -407,6 +426,7 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 	for (u64 k = 0; k < n; k++) {
 		if (off[k] > archive_len || len[k] > archive_len - off[k]) return ZG_ERR(ZG_error_srcSize_wrong);
 		if (out_off && out_off[k] != total) dense = false;
+		if (ulen[k] > UINT64_MAX - total) return ZG_ERR(ZG_error_dstSize_tooSmall);  // (the sum must not wrap)
 		total += ulen[k];
 	}
 	if (dense && total > out_cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
@@ -535,6 +555,11 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 	if (e1 != cudaSuccess || e2 != cudaSuccess) return ZG_ERR(ZG_error_device);
 	return first_err;
 }
+size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len, uint64_t n, const uint64_t* off,
+                       const uint64_t* len, const uint64_t* ulen, const uint8_t* digests, uint8_t* out, uint64_t out_cap,
+                       const uint64_t* out_off, uint8_t* ok, uint32_t* status) {
+	ZG_GUARD(unpack_batch_impl(d, archive, archive_len, n, off, len, ulen, digests, out, out_cap, out_off, ok, status));
+}
 
 size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t n) {
 	ZG_NEED_DEVICE();
@@ -584,7 +609,7 @@ size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t 
 // DCtx::decompress_stream contract (decode/zstd_iterator.rs:104-107,126-129): consume input until the
 // frame is complete, decode it on the GPU, then hand the output out as space allows.  Returns 0
 // when the frame is fully decoded and flushed, otherwise a non-zero hint.
-size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* input) {
+static size_t decompress_stream_impl(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* input) {
 	ZG_NEED_DEVICE();
 	if (!d || !output || !input) return ZG_ERR(ZG_error_GENERIC);
 	if (input->pos > input->size || output->pos > output->size) return ZG_ERR(ZG_error_srcSize_wrong);
@@ -629,6 +654,19 @@ size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* inp
 		return 0;
 	}
 	return d->out_acc.size() - d->out_pos;
+}
+size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* input) {
+	try {
+		return decompress_stream_impl(d, output, input);
+	} catch (...) {  // host staging could not be allocated: drop the half-collected frame, report it libzstd's way
+		if (d) {
+			d->in_acc.clear();
+			d->out_acc.clear();
+			d->out_pos = 0;
+			d->stage = 0;
+		}
+		return ZG_ERR(ZG_error_memory_allocation);
+	}
 }
 
 }  // extern "C"

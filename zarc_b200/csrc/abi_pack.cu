@@ -27,6 +27,14 @@ int zg_abi_dev_count();  // abi.cu
 	do {               \
 		if ((expr) != cudaSuccess) return ZG_ERR(ZG_error_memory_allocation); \
 	} while (0)
+#define ZG_GUARD(expr)                                    \
+	try {                                                 \
+		return (expr);                                    \
+	} catch (const std::bad_alloc&) {                     \
+		return ZG_ERR(ZG_error_memory_allocation);        \
+	} catch (...) {                                       \
+		return ZG_ERR(ZG_error_GENERIC);                  \
+	}
 
 // pack.cu
 size_t zg_pk_dedup_insert(cudaStream_t s, const u8* g_digest, u64 lo, u64 hi, u32* table, u32 mask);
@@ -96,7 +104,35 @@ static cudaError_t grow_keep(ZgBuf& b, size_t need, size_t keep, cudaStream_t s)
 	return cudaSuccess;
 }
 
+// Undo everything a failed batch did to the Encoder state: the map goes back to the ids below `nfiles0` (the table is
+// rebuilt from the kept digests -- open addressing has no cheap delete) and the running offset to `offset0`, so a
+// retry sees exactly the state the failed call started from.
+static void archive_rollback(zg_cctx* c, ZgArchive& A, u64 nfiles0, u64 offset0) {
+	cudaStream_t s = c->stream;
+	A.nfiles = nfiles0;
+	A.offset = offset0;
+	if (A.table_size) {
+		cudaMemsetAsync(A.table.p, 0, (size_t)A.table_size * 4, s);
+		if (nfiles0) zg_pk_dedup_insert(s, A.g_digest.as<u8>(), 0, nfiles0, A.table.as<u32>(), A.table_size - 1);
+		cudaStreamSynchronize(s);
+	}
+}
+
+static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
+                             u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes);
+// one batch, all or nothing: on any error the archive state is what it was on entry
 static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
+                        u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes) {
+	u64 nfiles0 = A.nfiles, offset0 = A.offset;
+	size_t r = pack_core_body(c, A, blob, off, len, F, digests_out, first_out, frame_off_out, frame_len_out, frames_out, frames_cap, frames_bytes);
+	if (zg_is_error(r)) {
+		archive_rollback(c, A, nfiles0, offset0);
+		if (frames_bytes) *frames_bytes = 0;
+	}
+	return r;
+}
+
+static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
                         u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes) {
 	cudaStream_t s = c->stream;
 	if (frames_bytes) *frames_bytes = 0;
@@ -382,6 +418,7 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 	const bool trace = getenv("ZG_TRACE") != nullptr;
 	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	double t_begin = now_ms();
+	const u64 nfiles0 = A.nfiles, offset0 = A.offset;  // the call is all or nothing, however many slices went through
 	size_t r = upload(0);
 	u64 written = 0;
 	for (size_t k = 0; k < sl.size() && !zg_is_error(r); k++) {
@@ -427,8 +464,11 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 	}
 	cudaError_t e1 = cudaStreamSynchronize(c->s_in), e2 = cudaStreamSynchronize(c->s_out);
 	if (trace) fprintf(stderr, "[zg pack] all results on the host at +%.2f ms\n", now_ms() - t_begin);
-	if (zg_is_error(r)) return r;
-	if (e1 != cudaSuccess || e2 != cudaSuccess) return ZG_ERR(ZG_error_device);
+	if (!zg_is_error(r) && (e1 != cudaSuccess || e2 != cudaSuccess)) r = ZG_ERR(ZG_error_device);
+	if (zg_is_error(r)) {
+		archive_rollback(c, A, nfiles0, offset0);
+		return r;
+	}
 	if (frames_bytes) *frames_bytes = written;
 	return 0;
 }
@@ -438,7 +478,7 @@ size_t zg_pack_batch(zg_cctx* c, const uint8_t* blob, const uint64_t* off, const
                      uint64_t* frames_bytes) {
 	ZG_NEED_DEVICE();
 	if (!c) return ZG_ERR(ZG_error_GENERIC);
-	return pack_host(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes);
+	ZG_GUARD(pack_host(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes));
 }
 
 // CCtx::compress2 (lowlevel_frames.rs:30): one complete frame, no dedup, no archive state.
@@ -453,8 +493,12 @@ size_t zg_compress2(zg_cctx* c, void* dst, size_t cap, const void* src, size_t n
 	if (A.table_size) ZG_CUDA(cudaMemsetAsync(A.table.p, 0, (size_t)A.table_size * 4, c->stream));
 	uint64_t off = 0, len = n, bytes = 0;
 	static const uint8_t empty = 0;
-	size_t r = pack_host(c, A, src ? (const uint8_t*)src : &empty, &off, &len, 1, nullptr, nullptr, nullptr, nullptr, (uint8_t*)dst, cap,
-	                     &bytes);
+	size_t r;
+	try {
+		r = pack_host(c, A, src ? (const uint8_t*)src : &empty, &off, &len, 1, nullptr, nullptr, nullptr, nullptr, (uint8_t*)dst, cap, &bytes);
+	} catch (...) {
+		return ZG_ERR(ZG_error_memory_allocation);
+	}
 	if (zg_is_error(r)) return r;
 	return bytes;
 }

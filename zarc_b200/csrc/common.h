@@ -55,6 +55,16 @@ struct ZgHostBuf {  // grow-only pinned host buffer
 };
 
 int zg_sm_count();
+// function attributes (opt-in shared memory) are per device: one flag per device, not one per process
+struct ZgPerDevice {
+	bool done[64] = {};
+	bool* slot() {
+		static bool never = false;
+		int d = 0;
+		if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return &(never = false);
+		return &done[d];
+	}
+};
 
 // ---- blake3.cu ----
 struct ZgB3Work {
@@ -106,6 +116,7 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 // ---- glue.cu ----
 size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off, const u64* ulen, const u64* produced,
                               const u32* cksums, u32* status, u64 n, int verify);
+size_t zg_verify_spans_run(cudaStream_t s, const u32* status, const u64* out_off, const u64* ulen, u64 out_cap, u64 n, u64* voff, u64* vlen);
 size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n);
 size_t zg_first_error_run(cudaStream_t s, const u32* status, u64 n, u64* first);
 

@@ -31,6 +31,19 @@ k_unpack_checksum_warp(const u8* __restrict__ out, const u64* __restrict__ out_o
 	if ((threadIdx.x & 31) == 0 && (u32)h != cksums[2 * k]) status[k] = ZS_E_CHECKSUM;
 }
 
+// what BLAKE3 verification may read: only frames that decoded (a frame rejected with dstSize_tooSmall / srcSize_wrong
+// has an output span that may lie outside `out`); the others are hashed as empty inputs at offset 0
+__global__ void __launch_bounds__(128)
+k_verify_spans(const u32* __restrict__ status, const u64* __restrict__ out_off, const u64* __restrict__ ulen, u64 out_cap, u64 n,
+               u64* __restrict__ voff, u64* __restrict__ vlen) {
+	u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	u64 o = out_off[k], l = ulen[k];
+	bool good = status[k] == ZS_OK && o <= out_cap && l <= out_cap - o;
+	voff[k] = good ? o : 0;
+	vlen[k] = good ? l : 0;
+}
+
 // ok[k] = frame decoded and BLAKE3(out_k) == expected  (FrameIterator::verify, frame_iterator.rs:86-88)
 __global__ void __launch_bounds__(128)
 k_digest_compare(const u8* __restrict__ got, const u8* __restrict__ want, const u32* __restrict__ status, u8* __restrict__ ok, u64 n) {
@@ -58,6 +71,12 @@ size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off,
 		ZG_LAUNCH(k_unpack_checksum_warp, (u32)((n + 3) / 4), 128, 0, s, out, out_off, ulen, cksums, status, n);
 		ZG_COUNT_LAUNCH();
 	}
+	return 0;
+}
+size_t zg_verify_spans_run(cudaStream_t s, const u32* status, const u64* out_off, const u64* ulen, u64 out_cap, u64 n, u64* voff, u64* vlen) {
+	if (!n) return 0;
+	ZG_LAUNCH(k_verify_spans, (u32)((n + 127) / 128), 128, 0, s, status, out_off, ulen, out_cap, n, voff, vlen);
+	ZG_COUNT_LAUNCH();
 	return 0;
 }
 size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n) {

@@ -1302,7 +1302,8 @@ static size_t zd_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 arch
 		perm = w.perm.as<u32>();
 	}
 	size_t smem = sizeof(ZdWarp) * ZD_WARPS;
-	static bool attr_set = false;
+	static ZgPerDevice attr_dev;
+	bool& attr_set = *attr_dev.slot();
 	if (!attr_set) {
 		if (cudaFuncSetAttribute(k_zstd_decode_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
 			return ZG_ERR(ZG_error_device);

@@ -1680,7 +1680,8 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	size_t smem_m = sizeof(ZeMatchWarp) * ZE_WARPS;
 	size_t smem_l = sizeof(ZeWarp) * ZE_WARPS;
 	size_t smem_q = sizeof(ZeWarp) * ZE_WARPS + sizeof(ZePredef);
-	static bool attr_set = false;
+	static ZgPerDevice attr_dev;
+	bool& attr_set = *attr_dev.slot();
 	if (!attr_set) {
 		if (cudaFuncSetAttribute(k_zstd_match_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess ||
 		    cudaFuncSetAttribute(k_zstd_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess ||

@@ -253,7 +253,8 @@ static void set_metadata(const File& entry, const std::string& path) {
 		gid_t gid = entry.group && entry.group->id ? (gid_t)*entry.group->id : (gid_t)-1;
 		if (chown(path.c_str(), uid, gid) != 0 && errno != EPERM) fprintf(stderr, "warning: chown %s: %s\n", path.c_str(), strerror(errno));
 	}
-	if (entry.mode && chmod(path.c_str(), *entry.mode & 07777) != 0) fprintf(stderr, "warning: chmod %s: %s\n", path.c_str(), strerror(errno));
+	// setuid / setgid bits of an untrusted archive are not restored (the reference applies the mode verbatim)
+	if (entry.mode && chmod(path.c_str(), *entry.mode & 01777) != 0) fprintf(stderr, "warning: chmod %s: %s\n", path.c_str(), strerror(errno));
 	if (entry.timestamps) {
 		timespec ts[2];
 		ts[0].tv_nsec = ts[1].tv_nsec = UTIME_OMIT;
@@ -286,7 +287,7 @@ static int cmd_unpack(int argc, char** argv) {
 			}
 		} else fprintf(stderr, "digest: %s\n", zarc.trailer().digest.base64().c_str());
 		zarc.read_directory();
-		uint64_t unpacked = 0;
+		uint64_t unpacked = 0, skipped = 0;
 		std::vector<const File*> batch;
 		std::vector<Digest> digests;
 		uint64_t batch_bytes = 0;
@@ -294,7 +295,7 @@ static int cmd_unpack(int argc, char** argv) {
 			if (batch.empty()) return;
 			std::vector<ContentFrame> frames = zarc.read_content_frames(digests);
 			for (size_t i = 0; i < batch.size(); i++) {
-				std::string path = batch[i]->name.to_path();
+				std::string path = *batch[i]->name.to_safe_path();  // checked when the entry was queued
 				fs::path parent = fs::path(path).parent_path();
 				if (!parent.empty()) fs::create_directories(parent);  // in case its entry wasn't in the zarc
 				std::FILE* f = fopen(path.c_str(), "wb");
@@ -313,8 +314,16 @@ static int cmd_unpack(int argc, char** argv) {
 			batch_bytes = 0;
 		};
 		for (const File& entry : zarc.files()) {
-			std::string name = entry.name.to_path();
-			if (!matches(filters, name)) continue;
+			std::string shown = entry.name.to_path();
+			if (!matches(filters, shown)) continue;
+			std::optional<std::string> safe = entry.name.to_safe_path();
+			if (!safe) {
+				// never write outside the extraction directory: "..", absolute and '/'-holding components are refused
+				fprintf(stderr, "warning: skipping entry with unsafe path: %s\n", shown.c_str());
+				skipped++;
+				continue;
+			}
+			const std::string& name = *safe;
 			if (entry.is_dir()) {
 				fs::create_directories(name);
 				set_metadata(entry, name);
@@ -333,6 +342,7 @@ static int cmd_unpack(int argc, char** argv) {
 		flush();
 		lap("read_content_frames (GPU) + write files");
 		fprintf(stderr, "unpacked %llu files\n", (unsigned long long)unpacked);
+		if (skipped) fprintf(stderr, "skipped %llu entries with unsafe paths\n", (unsigned long long)skipped);
 	} catch (const std::exception& e) {
 		fprintf(stderr, "error: %s\n", e.what());
 		return 1;

@@ -245,6 +245,22 @@ std::string Pathname::to_path() const {
 	return s;
 }
 
+// The extraction path of an entry read from an (untrusted) archive: "." and empty components are dropped, and a
+// component that is "..", holds a '/' or a NUL byte makes the whole name unsafe (nullopt).  Deliberate divergence
+// from the reference, whose unpack.rs:60-62 hands Pathname::to_path() to the filesystem verbatim (".." kept, an
+// absolute component replaces the path): that is an arbitrary-file-overwrite primitive for a hostile .zarc.
+std::optional<std::string> Pathname::to_safe_path() const {
+	std::string s;
+	for (const auto& c : components) {
+		if (c.data.empty() || c.data == ".") continue;
+		if (c.data == ".." || c.data.find('/') != std::string::npos || c.data.find('\0') != std::string::npos) return std::nullopt;
+		if (!s.empty()) s += '/';
+		s += c.data;
+	}
+	if (s.empty()) return std::nullopt;
+	return s;
+}
+
 // ================================================================================================
 // timestamps.rs
 static int64_t days_from_civil(int64_t y, unsigned m, unsigned d) {
@@ -537,6 +553,9 @@ void parse_directory_stream(const uint8_t* p, size_t n, Directory& out) {
 				else if (k == 4) f.uncompressed = r.uint();
 				else r.skip();
 			}
+			// the digest is untrusted input: its length is fixed by the digest type (integrity.rs:98-107), and the
+			// decoder copies exactly that many bytes out of it
+			if (f.digest.bytes.size() != DIGEST_LEN) throw Error("parse error: frame digest has the wrong length");
 			Digest key = f.digest;
 			out.frames[key] = std::move(f);
 		} else if (kind == (uint8_t)ElementKind::File) {
@@ -560,6 +579,7 @@ void parse_directory_stream(const uint8_t* p, size_t n, Directory& out) {
 				else if (k == 12) f.extended_attributes = get_attributes(r);
 				else r.skip();
 			}
+			if (f.digest && f.digest->bytes.size() != DIGEST_LEN) throw Error("parse error: file digest has the wrong length");
 			size_t index = out.files.size();
 			out.files_by_name[f.name].push_back(index);
 			if (f.digest) out.files_by_digest[*f.digest].push_back(index);
@@ -771,6 +791,7 @@ File Encoder::build_file_with_metadata(const std::string& path, bool follow_syml
 }
 
 void Encoder::add_file_entry(File entry) {
+	if (entry.digest && entry.digest->bytes.size() != DIGEST_LEN) throw Error("file entry digest has the wrong length");
 	if (entry.digest && !frames_.count(*entry.digest)) throw Error("cannot add file entry referencing unknown data frame");
 	size_t index = files_.size();
 	files_by_name_[entry.name].push_back(index);
@@ -948,6 +969,9 @@ std::vector<ContentFrame> Decoder::read_content_frames(const std::vector<Digest>
 		const Frame* f = frame(digests[i]);
 		if (!f) throw Error("frame not found");
 		if (f->offset > file_length_ || f->length > file_length_ - f->offset) throw Error("parse error: frame outside the file");
+		if (f->digest.bytes.size() != DIGEST_LEN) throw Error("parse error: frame digest has the wrong length");
+		// sizes come from the (untrusted) directory: the running totals must not wrap
+		if (f->uncompressed > UINT64_MAX - ubytes || f->length > UINT64_MAX - cbytes) throw Error("parse error: frame sizes overflow");
 		off[i] = cbytes;
 		len[i] = f->length;
 		ulen[i] = f->uncompressed;

@@ -60,6 +60,7 @@ struct Pathname {
 	std::vector<CborString> components;
 	static Pathname from_normal_components(const std::string& path);  // strings.rs:22-35
 	std::string to_path() const;                                      // strings.rs:38-62
+	std::optional<std::string> to_safe_path() const;                  // extraction: no "..", no absolute or '/'-holding components
 	bool operator<(const Pathname& o) const { return components < o.components; }
 	bool operator==(const Pathname& o) const { return components == o.components; }
 };
