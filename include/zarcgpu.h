@@ -138,6 +138,17 @@ size_t zg_pack_batch_dev(zg_cctx*, const uint8_t* blob, const uint64_t* off, con
                          uint8_t* digests, uint8_t* first, uint64_t* frame_off, uint64_t* frame_len,
                          uint8_t* frames_out, uint64_t frames_cap, uint64_t* frames_bytes /* HOST */);
 
+/* add_data_frame with its two decisions supplied by the caller, for archives packed by several GPUs (one rank per
+ * GPU, files sharded): `digests_in` (NULL: compute here) are the BLAKE3 digests of content_frame.rs:26,
+ * which the ranks need BEFORE this call to take the first-occurrence decision of content_frame.rs:30 over the global
+ * file order (zg_dedup_dev on the all-gathered digests); `select[i]` (NULL: all ones) is that decision.  A file with
+ * select[i] == 0 gets no frame here: first[i] = 0, and frame_off[i] / frame_len[i] name the frame of an earlier identical
+ * file of this context if there is one, else 0 / 0.  Device pointers. */
+size_t zg_pack_batch_dev_ex(zg_cctx*, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n_files,
+                            const uint8_t* digests_in, const uint8_t* select, uint8_t* digests, uint8_t* first,
+                            uint64_t* frame_off, uint64_t* frame_len, uint8_t* frames_out, uint64_t frames_cap,
+                            uint64_t* frames_bytes /* HOST */);
+
 /* zg_unpack_batch == for each entry k: Decoder::read_content_frame -> FrameIterator drained
  * (decode/frame_iterator.rs:14-27,94-103) + verify() (:77,86-88).
  *   archive[off[k] .. off[k]+len[k])  one Zstandard frame (Frame.offset / Frame.length)

@@ -23,18 +23,19 @@ def _free_port():
     return p
 
 
-def _files():
+def _files(dups=True):
     from tests.golden.recipes import text, rand
 
     fs = [text(3000 + 137 * i, i) if i % 3 else rand(500 + 91 * i, i) for i in range(14)]
-    fs[5] = fs[1]  # duplicates that land on different ranks
-    fs[9] = fs[2]
-    fs[12] = fs[1]
+    if dups:
+        fs[5] = fs[1]  # duplicates that land on different ranks
+        fs[9] = fs[2]
+        fs[12] = fs[1]
     fs.append(b"")
     return fs
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode="greedy", dups=True):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -42,9 +43,10 @@ def _worker(rank, world, port, q):
     from zarc_b200 import _lib, build, parallel
 
     lib = _lib.Lib(build.build_emu(), strict=False)
-    files = _files()
+    files = _files(dups)
     lens = np.array([len(f) for f in files], dtype=np.uint64)
-    plan = parallel.ShardPlan(lens, world)
+    plan = parallel.ShardPlan(lens, world, mode=mode)
+    assert plan.contiguous == (mode == "contiguous")
     mine = plan.mine(rank)
     local = [files[i] for i in mine]
     blob, off, ln = layout(local, 16)
@@ -56,36 +58,39 @@ def _worker(rank, world, port, q):
     lib.check(lib.zg_blake3_batch_dev(0, d_blob.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), n, dig.data_ptr()))
     # (2) global first-occurrence decisions
     first_l, rep_l, first_g, rep_g = parallel.global_dedup(lib, plan, dig)
-    # (3) encode only the local files that are global first occurrences
-    keep = torch.nonzero(first_l).flatten()
-    k = int(keep.numel())
+    # (3) encode the local files that are global first occurrences: add_data_frame with the digest (content_frame.rs:26)
+    #     and the first-occurrence decision (:30) handed in
     cctx = lib.zg_cctx_create()
     lib.check(lib.zg_cctx_init(cctx, 0))
     lib.check(lib.zg_cctx_set_parameter(cctx, 201, 1))
     lib.check(lib.zg_cctx_reset_archive(cctx, 0))
-    k_off, k_len = d_off[keep].contiguous(), d_len[keep].contiguous()
-    cap = int(k_len.sum()) + 4096 + 64 * k
+    cap = int(d_len.sum()) + 4096 + 64 * n
     frames = torch.zeros(cap, dtype=torch.uint8)
-    foff = torch.zeros(max(k, 1), dtype=torch.int64)
-    flen = torch.zeros(max(k, 1), dtype=torch.int64)
+    foff = torch.zeros(max(n, 1), dtype=torch.int64)
+    flen = torch.zeros(max(n, 1), dtype=torch.int64)
+    first_out = torch.zeros(max(n, 1), dtype=torch.uint8)
     nbytes = np.zeros(1, dtype=np.uint64)
-    lib.check(lib.zg_pack_batch_dev(cctx, d_blob.data_ptr(), k_off.data_ptr(), k_len.data_ptr(), k, None, None, foff.data_ptr(),
-                                    flen.data_ptr(), frames.data_ptr(), cap, nbytes.ctypes.data))
+    sel = first_l.contiguous()
+    lib.check(lib.zg_pack_batch_dev_ex(cctx, d_blob.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), n, dig.data_ptr(), sel.data_ptr(), None,
+                                       first_out.data_ptr(), foff.data_ptr(), flen.data_ptr(), frames.data_ptr(), cap, nbytes.ctypes.data))
     lib.zg_cctx_free(cctx)
-    local_flen = torch.zeros(n, dtype=torch.int64)
-    local_flen[keep] = flen[:k]
+    assert torch.equal(first_out[:n], sel)
+    local_flen = flen[:n] * sel.to(torch.int64)  # (an unselected file answers with an earlier local copy's frame, if any, else 0)
+    keep = torch.nonzero(first_l).flatten()
     # (4) global archive offsets
-    g_off, g_len, total = parallel.global_offsets(lib, plan, local_flen, first_g, rep_g, base=12)
+    g_off, g_len, total = parallel.global_offsets(lib, plan, local_flen, first_g, rep_g, base=12, no_duplicates=not dups)
+    total = int(total)
     # ship everything to the parent for checking
     local_frames = {}
     for j, i in enumerate(keep.tolist()):
-        local_frames[int(mine[i])] = bytes(frames[int(foff[j]) : int(foff[j]) + int(flen[j])].numpy())
+        local_frames[int(mine[i])] = bytes(frames[int(foff[i]) : int(foff[i]) + int(flen[i])].numpy())
     q.put((rank, mine.tolist(), [bytes(d.numpy()) for d in dig], first_l.tolist(), g_off.tolist(), g_len.tolist(), total, local_frames))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_pack_matches_serial_reference():
+@pytest.mark.parametrize("mode,dups", [("greedy", True), ("contiguous", True), ("contiguous", False)])
+def test_two_rank_sharded_pack_matches_serial_reference(mode, dups):
     from oracle import ref_path
     from zarc_b200 import build
 
@@ -93,14 +98,14 @@ def test_two_rank_sharded_pack_matches_serial_reference():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, dups)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=300) for _ in range(world)]
+    results = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    files = _files()
+    files = _files(dups)
     n = len(files)
     digest, first, off, ln, frames = [None] * n, [None] * n, [None] * n, [None] * n, {}
     total = None
@@ -146,3 +151,24 @@ def test_partition_is_balanced_and_complete():
             assert np.all(np.diff(p) > 0)  # input order preserved inside a rank
     c3 = corpus.c3_huge(n_files=8, file_bytes=1 << 20)
     assert sorted(len(p) for p in corpus.partition_balanced(c3.len, 8)) == [1] * 8
+
+
+def test_contiguous_partition_and_plan_choice():
+    from zarc_b200 import corpus, parallel
+
+    c = corpus.c2_source_tree(total_bytes=50_000_000, seed=4)
+    for world in (1, 2, 4, 8):
+        parts = parallel.partition_contiguous(c.len, world)
+        assert np.array_equal(np.concatenate(parts), np.arange(c.n_files))
+        sizes = [int(c.len[p].sum()) for p in parts]
+        assert max(sizes) - min(sizes) <= 2 * 65536
+    assert parallel.ShardPlan(c.len, 8).contiguous  # many small files: contiguous ranges are even
+    c3 = corpus.c3_huge(n_files=8, file_bytes=1 << 20)
+    assert [len(p) for p in parallel.partition_contiguous(c3.len, 8)] == [1] * 8
+    # sizes sorted descending: contiguous ranges cannot be even, the plan falls back to the greedy deal
+    skew = np.sort(c.len[:64])[::-1].copy()
+    plan = parallel.ShardPlan(skew, 8)
+    assert parallel.ShardPlan(np.array([1 << 20, 10, 10, 10], dtype=np.uint64), 2).contiguous is False
+    assert np.array_equal(np.sort(np.concatenate(plan.parts)), np.arange(64))
+    empty = parallel.partition_contiguous(np.zeros(5, dtype=np.uint64), 2)
+    assert np.array_equal(np.concatenate(empty), np.arange(5))

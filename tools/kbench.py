@@ -57,6 +57,30 @@ def main():
     off, ln = dev(c.off), dev(c.len)
     n = c.n_files
     s = torch.cuda.current_stream().cuda_stream
+    if "intpeak" in args.what:
+        import ctypes as C
+
+        f = lib.dll.zg_internal_int_peak
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        peak = {}
+        for mode, name in enumerate(["iadd3", "lop3", "shf", "prmt", "blake3_g_mix"]):
+            best = 0.0
+            for ctas in (4, 8):
+                for _ in range(3):
+                    ms, th, ops = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+                    lib.check(f(s, mode, 20000, ctas, C.byref(ms), C.byref(th), C.byref(ops)))
+                    best = max(best, th.value * ops.value / (ms.value * 1e-3))
+            peak[name] = best
+        res["int_peak_lane_ops_per_s"] = peak
+        sm = torch.cuda.get_device_properties(0).multi_processor_count
+        res["int_peak_lane_ops_per_clk_per_sm_at_1965MHz"] = {k: v / sm / 1.965e9 for k, v in peak.items()}
+        json.dump({"int32_lane_ops_per_s": peak["blake3_g_mix"], "single_op_lane_instr_per_s": {k: peak[k] for k in ("iadd3", "lop3", "shf", "prmt")},
+                   "sms": sm,
+                   "how": "tools/kbench.py --what intpeak: zarc_b200/csrc/peak.cu, 8 independent chains per thread, 256 threads x 4-8 CTAs per SM, "
+                          "best of 3, CUDA events; the figure used as the INT32 roofline is the BLAKE3 quarter-round mix (add3 / xor / rotates by "
+                          "16 and 12), operations counted as SURVEY.md App. B counts BLAKE3's 792 per compression"},
+                  open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "int_peak.json"), "w"))
     if "pcie" in args.what:
         # host link: pinned copies, each direction alone and both at once (what bounds the e2e number)
         nb = 1 << 30

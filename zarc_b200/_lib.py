@@ -53,6 +53,7 @@ SIGNATURES = {
     "zg_cctx_archive_offset": (_u64, [_vp]),
     "zg_pack_batch": (_sz, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "zg_pack_batch_dev": (_sz, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "zg_pack_batch_dev_ex": (_sz, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "zg_unpack_batch": (_sz, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "zg_unpack_batch_dev": (_sz, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "zg_blake3_batch_dev": (_sz, [_vp, _vp, _vp, _vp, _u64, _vp]),

@@ -108,6 +108,21 @@ def build_host(force: bool = False) -> str:
     return HOST_BIN
 
 
+CORPUS_SO = os.path.join(ROOT, "tools", "libzarc_corpus.so")
+
+
+def build_corpus_host(force: bool = False) -> str:
+    """g++ -> tools/libzarc_corpus.so: the corpus generator alone, for the CPU reference arm of bench.py (which must
+    not load the product library)."""
+    src = os.path.join(ROOT, "tools", "corpus_host.cpp")
+    deps = [src, os.path.join(CSRC, "corpus.cuh"), os.path.join(CSRC, "simt.h")]
+    if not force and os.path.exists(CORPUS_SO) and os.path.getmtime(CORPUS_SO) >= max(os.path.getmtime(f) for f in deps):
+        return CORPUS_SO
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DZG_EMU", "-I", EMU_DIR, "-I", CSRC, "-Wno-unused-function",
+                           src, "-o", CORPUS_SO])
+    return CORPUS_SO
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["product"]
     if "product" in which:
@@ -116,3 +131,5 @@ if __name__ == "__main__":
         print(build_emu(force="--force" in which))
     if "host" in which:
         print(build_host(force="--force" in which))
+    if "corpus" in which:
+        print(build_corpus_host(force="--force" in which))

@@ -38,8 +38,8 @@ int zg_abi_dev_count();  // abi.cu
 
 // pack.cu
 size_t zg_pk_dedup_insert(cudaStream_t s, const u8* g_digest, u64 lo, u64 hi, u32* table, u32 mask);
-size_t zg_pk_dedup_resolve(cudaStream_t s, const u8* g_digest, u64 base, u64 n, const u32* table, u32 mask, const u64* len, u64* rep,
-                           u8* first, u64* isfirst64, u64* nblk, u64* clen);
+size_t zg_pk_dedup_resolve(cudaStream_t s, const u8* g_digest, u64 base, u64 n, const u32* table, u32 mask, const u64* len, const u8* select,
+                           u64* rep, u8* first, u64* isfirst64, u64* nblk, u64* clen);
 size_t zg_pk_build_ulist(cudaStream_t s, const u8* first, const u64* uidx, const u64* blk_first, u64 n, u32* ulist, u64* blk_base,
                          u64 nuniq, u64 nblocks);
 size_t zg_pk_block_out_sizes(cudaStream_t s, const u32* blk_csize, u64 nblocks, u64* blk_out);
@@ -119,12 +119,15 @@ static void archive_rollback(zg_cctx* c, ZgArchive& A, u64 nfiles0, u64 offset0)
 }
 
 static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
-                             u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes);
+                             u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes, const u8* digests_in,
+                             const u8* select);
 // one batch, all or nothing: on any error the archive state is what it was on entry
 static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
-                        u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes) {
+                        u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes,
+                        const u8* digests_in = nullptr, const u8* select = nullptr) {
 	u64 nfiles0 = A.nfiles, offset0 = A.offset;
-	size_t r = pack_core_body(c, A, blob, off, len, F, digests_out, first_out, frame_off_out, frame_len_out, frames_out, frames_cap, frames_bytes);
+	size_t r = pack_core_body(c, A, blob, off, len, F, digests_out, first_out, frame_off_out, frame_len_out, frames_out, frames_cap, frames_bytes,
+	                          digests_in, select);
 	if (zg_is_error(r)) {
 		archive_rollback(c, A, nfiles0, offset0);
 		if (frames_bytes) *frames_bytes = 0;
@@ -133,7 +136,8 @@ static size_t pack_core(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off
 }
 
 static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64* off, const u64* len, u64 F, u8* digests_out, u8* first_out,
-                        u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes) {
+                             u64* frame_off_out, u64* frame_len_out, u8* frames_out, u64 frames_cap, u64* frames_bytes, const u8* digests_in,
+                             const u8* select) {
 	cudaStream_t s = c->stream;
 	if (frames_bytes) *frames_bytes = 0;
 	if (F == 0) return 0;
@@ -147,9 +151,14 @@ static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64
 	ZG_ALLOC(grow_keep(A.g_off, (base + F) * 8, base * 8, s));
 	ZG_ALLOC(grow_keep(A.g_len, (base + F) * 8, base * 8, s));
 	u8* g_digest = A.g_digest.as<u8>();
-	// (1) digests (content_frame.rs:26)
-	ZG_TRY(zg_blake3_run(s, c->b3, blob, off, len, F, g_digest + 32 * base));
-	if (digests_out) ZG_CUDA(cudaMemcpyAsync(digests_out, g_digest + 32 * base, F * 32, cudaMemcpyDeviceToDevice, s));
+	// (1) digests (content_frame.rs:26) -- or the ones the caller already computed (multi-GPU: the digests are needed
+	//     before this call for the cross-rank first-occurrence decision)
+	if (digests_in) ZG_CUDA(cudaMemcpyAsync(g_digest + 32 * base, digests_in, F * 32, cudaMemcpyDeviceToDevice, s));
+	else ZG_TRY(zg_blake3_run(s, c->b3, blob, off, len, F, g_digest + 32 * base));
+	if (digests_out && digests_out != digests_in) ZG_CUDA(cudaMemcpyAsync(digests_out, g_digest + 32 * base, F * 32, cudaMemcpyDeviceToDevice, s));
+	// files that end up without a frame of their own in this archive part answer with offset 0 / length 0
+	ZG_CUDA(cudaMemsetAsync(A.g_off.as<u64>() + base, 0, F * 8, s));
+	ZG_CUDA(cudaMemsetAsync(A.g_len.as<u64>() + base, 0, F * 8, s));
 	// (2) dedup (content_frame.rs:30): the table keeps, per digest, the smallest global id
 	u64 want = 1024;
 	while (want < 2 * (base + F)) want <<= 1;
@@ -176,7 +185,7 @@ static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64
 		first = c->first_tmp.as<u8>();
 	}
 	u64* totals = c->totals.as<u64>();
-	ZG_TRY(zg_pk_dedup_resolve(s, g_digest, base, F, A.table.as<u32>(), A.table_size - 1, len, c->rep.as<u64>(), first,
+	ZG_TRY(zg_pk_dedup_resolve(s, g_digest, base, F, A.table.as<u32>(), A.table_size - 1, len, select, c->rep.as<u64>(), first,
 	                           c->isfirst64.as<u64>(), c->nblk.as<u64>(), c->clen.as<u64>()));
 	ZG_TRY(zg_scan_run(s, c->tiles, c->isfirst64.as<u64>(), F, 0, c->uidx.as<u64>(), totals + 0));
 	ZG_TRY(zg_scan_run(s, c->tiles, c->nblk.as<u64>(), F, 0, c->blkfirst.as<u64>(), totals + 1));
@@ -344,6 +353,19 @@ size_t zg_pack_batch_dev(zg_cctx* c, const uint8_t* blob, const uint64_t* off, c
 	ZG_NEED_DEVICE();
 	if (!c) return ZG_ERR(ZG_error_GENERIC);
 	return pack_core(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes);
+}
+
+// add_data_frame with its two decisions made by the caller (multi-GPU): `digests_in` (may be NULL)
+// are the files' BLAKE3 digests computed earlier (zg_blake3_batch_dev) -- the digest of content_frame.rs:26 is needed
+// before the cross-rank dedup -- and `select` (may be NULL) is the global "first occurrence" answer of
+// content_frame.rs:30 for each file: a file with select[i] == 0 gets no frame here (first[i] = 0, frame_len[i] = 0).
+size_t zg_pack_batch_dev_ex(zg_cctx* c, const uint8_t* blob, const uint64_t* off, const uint64_t* len, uint64_t n, const uint8_t* digests_in,
+                            const uint8_t* select, uint8_t* digests, uint8_t* first, uint64_t* frame_off, uint64_t* frame_len,
+                            uint8_t* frames_out, uint64_t frames_cap, uint64_t* frames_bytes) {
+	ZG_NEED_DEVICE();
+	if (!c) return ZG_ERR(ZG_error_GENERIC);
+	return pack_core(c, c->archive, blob, off, len, n, digests, first, frame_off, frame_len, frames_out, frames_cap, frames_bytes, digests_in,
+	                 select);
 }
 
 // Host-buffer pack.  The batch is cut into slices of about g_zg_pack_slice_bytes of input (in file order) that
@@ -521,7 +543,7 @@ extern "C" size_t zg_dedup_dev(void* stream, const uint8_t* digests, uint64_t n,
 		cudaMemsetAsync(tmp.p, 0, n * 8 * 4, s);
 		u64* t = tmp.as<u64>();
 		r = zg_pk_dedup_insert(s, digests, 0, n, table.as<u32>(), (u32)want - 1);
-		if (!r) r = zg_pk_dedup_resolve(s, digests, 0, n, table.as<u32>(), (u32)want - 1, t, rep, first, t + n, t + 2 * n, t + 3 * n);
+		if (!r) r = zg_pk_dedup_resolve(s, digests, 0, n, table.as<u32>(), (u32)want - 1, t, nullptr, rep, first, t + n, t + 2 * n, t + 3 * n);
 		if (cudaStreamSynchronize(s) != cudaSuccess) r = ZG_ERR(ZG_error_device);
 	}
 	table.release();

@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(128) k_dedup_insert(const u8* __restrict__ g_d
 // nblk[i] = number of Zstandard blocks to encode for i (0 for duplicates)
 __global__ void __launch_bounds__(128)
 k_dedup_resolve(const u8* __restrict__ g_digest, u64 base, u64 n, const u32* __restrict__ table, u32 mask,
-                const u64* __restrict__ len, u64* __restrict__ rep, u8* __restrict__ first, u64* __restrict__ isfirst64,
-                u64* __restrict__ nblk, u64* __restrict__ clen) {
+                const u64* __restrict__ len, const u8* __restrict__ select, u64* __restrict__ rep, u8* __restrict__ first,
+                u64* __restrict__ isfirst64, u64* __restrict__ nblk, u64* __restrict__ clen) {
 	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	u64 id = base + i;
@@ -56,7 +56,7 @@ k_dedup_resolve(const u8* __restrict__ g_digest, u64 base, u64 n, const u32* __r
 		slot = (slot + 1) & mask;
 	}
 	u64 r = cur - 1;
-	bool f = r == id;
+	bool f = r == id && (!select || select[i]);  // (select: the decision was taken over more files than this context has seen)
 	rep[i] = r;
 	first[i] = f ? 1 : 0;
 	isfirst64[i] = f ? 1 : 0;
@@ -251,9 +251,9 @@ size_t zg_pk_dedup_insert(cudaStream_t s, const u8* g_digest, u64 lo, u64 hi, u3
 	ZG_COUNT_LAUNCH();
 	return 0;
 }
-size_t zg_pk_dedup_resolve(cudaStream_t s, const u8* g_digest, u64 base, u64 n, const u32* table, u32 mask, const u64* len, u64* rep,
-                           u8* first, u64* isfirst64, u64* nblk, u64* clen) {
-	ZG_LAUNCH(k_dedup_resolve, PK_GRID(n), 128, 0, s, g_digest, base, n, table, mask, len, rep, first, isfirst64, nblk, clen);
+size_t zg_pk_dedup_resolve(cudaStream_t s, const u8* g_digest, u64 base, u64 n, const u32* table, u32 mask, const u64* len, const u8* select,
+                           u64* rep, u8* first, u64* isfirst64, u64* nblk, u64* clen) {
+	ZG_LAUNCH(k_dedup_resolve, PK_GRID(n), 128, 0, s, g_digest, base, n, table, mask, len, select, rep, first, isfirst64, nblk, clen);
 	ZG_COUNT_LAUNCH();
 	return 0;
 }
