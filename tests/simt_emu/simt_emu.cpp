@@ -204,6 +204,12 @@ void warp_barrier(unsigned mask) {
 	g.tIdx = fibers[cur].tid;
 }
 
+void yield() {
+	fibers[cur].state = READY;
+	yield_to_sched();
+	g.tIdx = fibers[cur].tid;
+}
+
 void cta_barrier() {
 	cta_arrived++;
 	if (cta_arrived == n_alive) {

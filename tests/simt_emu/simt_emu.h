@@ -61,6 +61,8 @@ void cta_barrier();
 // exchange slots of the current warp (one 64-bit value per lane)
 unsigned long long* warp_slots();
 unsigned lane_id();
+// hand the processor to another fiber of the CTA (a spin-wait on what another warp writes must call this)
+void yield();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 }  // namespace zg_emu
 

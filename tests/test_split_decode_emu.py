@@ -1,6 +1,7 @@
-"""Block-parallel decoding of multi-block frames (zstd_decode.cu, k_zd_split_* / k_zd_join): frames whose blocks are
-independent (this library's encoder) decode block by block; any other frame is detected and decoded again serially.
-Either way the bytes equal the reference decoder's."""
+"""The staged pipeline for multi-block frames (zstd_decode_staged.cu): every block of every frame is entropy-decoded in
+parallel (tables inherited from earlier blocks, repeat offsets symbolic), then executed -- at once when the block reads
+nothing before itself (this library's encoder), after the blocks it reads otherwise (libzstd).  No frame is decoded twice,
+and the bytes equal the reference decoder's."""
 import ctypes as C
 import struct
 
@@ -22,6 +23,13 @@ def _b3(d):
 def _stats(lib):
     out = (C.c_uint64 * 3)()
     lib.dll.zg_internal_decode_stats(out)
+    return list(out)
+
+
+def _stats_ex(lib):
+    """{frames, work items, frames decoded twice, staged frames, staged blocks, blocks that waited for earlier output, chunks}"""
+    out = (C.c_uint64 * 8)()
+    lib.dll.zg_internal_decode_stats_ex(out)
     return list(out)
 
 
@@ -59,17 +67,33 @@ def test_own_multi_block_frames_decode_block_parallel(emu):
         assert ref_path.ref_decompress(fr, len(f)) == f
 
 
-def test_reference_multi_block_frames_fall_back_to_serial(emu):
+def test_reference_multi_block_frames_decode_staged_in_one_pass(emu):
     files = _files()
-    for level in (1, 3, 19):
+    for level in (1, 3, 9, 19):
         frames = [ref_path.ref_compress(f, level=level) for f in files]
         outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], [_b3(f) for f in files])
         assert rc == 0 and status == [0] * len(files)
         assert outs == files and ok == [1] * len(files)
         n_frames, n_items, n_redo = _stats(emu)
-        if level < 19:  # (level 19's block splitter makes blocks of other sizes: those frames are not even tried)
-            assert n_items > n_frames      # they were tried ...
-            assert n_redo >= 3             # ... and libzstd's text frames have matches across blocks
+        ex = _stats_ex(emu)
+        assert n_redo == 0                 # nothing is decoded twice
+        assert n_items > n_frames and ex[3] >= 5   # the multi-block frames went through the staged pipeline ...
+        assert ex[5] >= 3                  # ... and libzstd's text frames have blocks that read earlier blocks
+
+
+def test_chunked_staging_equals_one_pass(emu):
+    """Tiny chunks (a few blocks each): the per-frame state (output offset, repeat history, completion) carries over."""
+    files = _files()
+    try:
+        for chunk in (1, 3, 7):
+            emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(chunk))
+            for make in (lambda: _own_frames(emu, files), lambda: [ref_path.ref_compress(f, level=3) for f in files]):
+                frames = make()
+                outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], [_b3(f) for f in files])
+                assert rc == 0 and status == [0] * len(files) and outs == files and ok == [1] * len(files)
+            assert _stats_ex(emu)[6] >= 3
+    finally:
+        emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(0))
 
 
 def test_split_threshold_and_mixed_batch(emu):
@@ -103,18 +127,17 @@ def _raw_frame(parts, checksum=True):
 
 
 def test_short_blocks_are_not_mistaken_for_full_ones(emu):
-    # two blocks, the first one short: the split guess (block 1 starts at 128 KiB) is wrong and must be noticed
+    # blocks of other sizes than 128 KiB: every block's place comes from the prefix sum of the sizes before it
     f1, d1 = _raw_frame([rand(100_000, 1), rand(100_000, 2)])
-    # three blocks where ceil(n / 128 KiB) = 2: not split at all
     f2, d2 = _raw_frame([rand(1000, 3), rand(BLOCK, 4), rand(70_000, 5)])
-    # full blocks: accepted
+    # full blocks
     f3, d3 = _raw_frame([rand(BLOCK, 6), rand(BLOCK, 7), rand(5, 8)])
     for f, d in ((f1, d1), (f2, d2), (f3, d3)):
         assert ref_path.ref_decompress(f, len(d)) == d
     outs, ok, status, rc = unpack_batch(emu, [f1, f2, f3], [len(d1), len(d2), len(d3)], [_b3(d1), _b3(d2), _b3(d3)])
     assert rc == 0 and status == [0, 0, 0] and outs == [d1, d2, d3] and ok == [1, 1, 1]
     n_frames, n_items, n_redo = _stats(emu)
-    assert (n_frames, n_items, n_redo) == (3, 2 + 1 + 3, 1)
+    assert (n_frames, n_items, n_redo) == (3, 2 + 3 + 3, 0)  # blocks of any size are staged; nothing is decoded twice
 
 
 def test_corruption_inside_split_frames(emu):

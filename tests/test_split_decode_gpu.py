@@ -10,8 +10,12 @@ def test_own_multi_block_frames_decode_block_parallel(gpu):
     cases.test_own_multi_block_frames_decode_block_parallel(gpu)
 
 
-def test_reference_multi_block_frames_fall_back_to_serial(gpu):
-    cases.test_reference_multi_block_frames_fall_back_to_serial(gpu)
+def test_reference_multi_block_frames_decode_staged_in_one_pass(gpu):
+    cases.test_reference_multi_block_frames_decode_staged_in_one_pass(gpu)
+
+
+def test_chunked_staging_equals_one_pass(gpu):
+    cases.test_chunked_staging_equals_one_pass(gpu)
 
 
 def test_split_threshold_and_mixed_batch(gpu):

@@ -90,6 +90,19 @@ size_t zg_scan_run(cudaStream_t s, ZgBuf& tiles, const u64* in, u64 n, u64 base,
 cudaError_t zg_publish(cudaStream_t s, const void* dev_src, void* pinned_dst, u32 nbytes);  // small results -> pinned host memory, no copy engine
 
 // ---- zstd_decode.cu ----
+struct ZgZdStaged {  // the staged pipeline for multi-block frames (zstd_decode_staged.cu)
+	ZgBuf nblk, first, multi, single, tot, hist;                 // per frame: block count, first block; frame lists; totals; histogram
+	ZgBuf blk, res, out_pos, rep_in, dep, done;                  // per block
+	ZgBuf tail, f_out, f_rep, f_status, done_upto;               // per frame: running state across chunks
+	ZgBuf jbase, cursor, queue, items, seq_cnt, lit_cnt, seq_off, lit_off, seq_stage, lit_stage, tabs;  // per chunk
+	ZgHostBuf hh;
+	void release() {
+		for (ZgBuf* b : {&nblk, &first, &multi, &single, &tot, &hist, &blk, &res, &out_pos, &rep_in, &dep, &done, &tail, &f_out, &f_rep, &f_status,
+		                 &done_upto, &jbase, &cursor, &queue, &items, &seq_cnt, &lit_cnt, &seq_off, &lit_off, &seq_stage, &lit_stage, &tabs})
+			b->release();
+		hh.release();
+	}
+};
 struct ZgZdWork {
 	ZgBuf seqs;     // per-warp sequence arenas
 	ZgBuf lit;      // per-warp literal buffers
@@ -97,15 +110,12 @@ struct ZgZdWork {
 	ZgBuf hufsave;  // per-lane Huffman weights (Treeless blocks)
 	ZgBuf queue;    // frame queue counter
 	ZgBuf bins, perm;  // size-sorted hand-out order
-	// block-parallel decoding of multi-block frames: work items (a whole frame, or one block of a split frame)
-	ZgBuf nitems, ibase, tiles, total;  // per frame: item count and first item; scan scratch; totals {items, redo}
-	ZgBuf it_k, it_j, it_ip, it_len, it_status, it_prod;  // per item
-	ZgBuf tail, fabort, redo;  // per frame: offset past the last block, "a block failed" flag; frames to decode again serially
+	ZgBuf tiles;       // scan scratch
+	ZgZdStaged st;
 	ZgHostBuf h;
 	void release() {
-		for (ZgBuf* b : {&seqs, &lit, &tabs, &hufsave, &queue, &bins, &perm, &nitems, &ibase, &tiles, &total, &it_k, &it_j, &it_ip, &it_len,
-		                 &it_status, &it_prod, &tail, &fabort, &redo})
-			b->release();
+		for (ZgBuf* b : {&seqs, &lit, &tabs, &hufsave, &queue, &bins, &perm, &tiles}) b->release();
+		st.release();
 		h.release();
 	}
 };
