@@ -183,6 +183,47 @@ def ref_decompress_stream(archive: bytes, offset: int) -> bytes:
         _zstd.ZSTD_freeDCtx(dctx)
 
 
+def ref_stream_digest(archive, offset: int = 0):
+    """FrameIterator drained without keeping the bytes (decode/frame_iterator.rs:94-103: every chunk the streaming
+    decoder hands out goes into the Hasher; :77 finalize): returns (BLAKE3 digest, bytes produced, bytes consumed).
+    `archive` may be bytes or a numpy u8 array (multi-GiB frames)."""
+    import blake3
+    import numpy as np
+
+    if isinstance(archive, (bytes, bytearray)):
+        archive = np.frombuffer(archive, dtype=np.uint8)
+    base = archive.ctypes.data
+    total = int(archive.shape[0])
+    dctx = _zstd.ZSTD_createDCtx()
+    try:
+        in_size = max(_zstd.ZSTD_DStreamInSize(), 1024)
+        out_size = max(_zstd.ZSTD_DStreamOutSize(), 1024)
+        outmem = ctypes.create_string_buffer(out_size)
+        out_addr = ctypes.cast(outmem, _vp)
+        hasher = blake3.blake3(max_threads=1)
+        pos, produced, done = offset, 0, False
+        while not done:
+            avail = min(in_size, total - pos)
+            if avail <= 0:
+                raise ZstdError("unexpected end of archive")
+            inbuf = _Buf(base + pos, avail, 0)
+            while True:
+                outbuf = _Buf(out_addr, out_size, 0)
+                hint = _check(_zstd.ZSTD_decompressStream(dctx, ctypes.byref(outbuf), ctypes.byref(inbuf)))
+                if outbuf.pos:
+                    hasher.update(ctypes.string_at(out_addr, outbuf.pos))
+                    produced += outbuf.pos
+                if hint == 0:
+                    done = True
+                    break
+                if outbuf.pos < out_size and inbuf.pos == inbuf.size:
+                    break
+            pos += inbuf.pos
+        return hasher.digest(), produced, pos - offset
+    finally:
+        _zstd.ZSTD_freeDCtx(dctx)
+
+
 def ref_decompress(frame: bytes, max_out: int) -> bytes:
     """One-shot libzstd decode (the "reference zstd decoder" for GPU-made frames)."""
     dctx = _zstd.ZSTD_createDCtx()

@@ -87,6 +87,9 @@ struct zg_cctx {
 		cudaEvent_t in_done = nullptr, out_done = nullptr;
 	} stage[2];
 	cudaStream_t s_in = nullptr, s_out = nullptr;
+	// the Content_Checksum (XXH64: one serial multiply-rotate chain per file) runs beside the encoder, not after it
+	cudaStream_t s_xx = nullptr;
+	cudaEvent_t xx_fork = nullptr, xx_join = nullptr;
 };
 
 static cudaError_t grow_keep(ZgBuf& b, size_t need, size_t keep, cudaStream_t s) {
@@ -210,9 +213,30 @@ static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64
 		ZG_TRY(zg_pk_build_ulist(s, first, c->uidx.as<u64>(), c->blkfirst.as<u64>(), F, c->ulist.as<u32>(), c->blk_base.as<u64>(), nuniq,
 		                         nblocks));
 		// (3) compress every new content (content_frame.rs:41 -> lowlevel_frames.rs:30)
+		bool side = false;
+		if (c->checksum) {
+			// the checksums only need the input and the unique list: fork them onto a side stream (launched first, higher
+			// priority, so that its few long-running warps are resident while the encoder's kernels fill the rest)
+			if (!c->s_xx) {
+				int lo = 0, hi = 0;
+				cudaDeviceGetStreamPriorityRange(&lo, &hi);
+				if (cudaStreamCreateWithPriority(&c->s_xx, cudaStreamNonBlocking, hi) != cudaSuccess ||
+				    cudaEventCreateWithFlags(&c->xx_fork, cudaEventDisableTiming) != cudaSuccess ||
+				    cudaEventCreateWithFlags(&c->xx_join, cudaEventDisableTiming) != cudaSuccess)
+					c->s_xx = nullptr;
+			}
+			side = c->s_xx != nullptr;
+			if (side) {
+				ZG_CUDA(cudaEventRecord(c->xx_fork, s));
+				ZG_CUDA(cudaStreamWaitEvent(c->s_xx, c->xx_fork, 0));
+				ZG_TRY(zg_pk_xxh64_list(c->s_xx, blob, off, len, c->ulist.as<u32>(), nuniq, c->xxh.as<u64>()));
+				ZG_CUDA(cudaEventRecord(c->xx_join, c->s_xx));
+			}
+		}
 		ZG_TRY(zg_zstd_encode_run(s, c->ze, blob, off, c->comp_off.as<u64>(), len, c->ulist.as<u32>(), c->blk_base.as<u64>(), (u32)nuniq,
 		                          nblocks, comp_bytes, c->comp.as<u8>(), c->blk_csize.as<u32>(), c->level));
-		if (c->checksum) ZG_TRY(zg_pk_xxh64_list(s, blob, off, len, c->ulist.as<u32>(), nuniq, c->xxh.as<u64>()));
+		if (c->checksum && !side) ZG_TRY(zg_pk_xxh64_list(s, blob, off, len, c->ulist.as<u32>(), nuniq, c->xxh.as<u64>()));
+		if (side) ZG_CUDA(cudaStreamWaitEvent(s, c->xx_join, 0));
 		// (4) frame lengths -> archive offsets (content_frame.rs:22,45)
 		ZG_TRY(zg_pk_block_out_sizes(s, c->blk_csize.as<u32>(), nblocks, c->blk_out.as<u64>()));
 		ZG_TRY(zg_scan_run(s, c->tiles, c->blk_out.as<u64>(), nblocks, 0, c->blk_pos.as<u64>(), totals + 3));
@@ -273,6 +297,12 @@ void zg_cctx_free(zg_cctx* c) {
 	}
 	if (c->s_in) cudaStreamDestroy(c->s_in);
 	if (c->s_out) cudaStreamDestroy(c->s_out);
+	if (c->s_xx) {
+		cudaStreamSynchronize(c->s_xx);
+		cudaStreamDestroy(c->s_xx);
+		cudaEventDestroy(c->xx_fork);
+		cudaEventDestroy(c->xx_join);
+	}
 	c->h.release();
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;

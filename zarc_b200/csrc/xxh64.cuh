@@ -14,6 +14,35 @@ ZG_DEV u64 xx_rotl(u64 x, int n) { return (x << n) | (x >> (64 - n)); }
 ZG_DEV u64 xx_round(u64 acc, u64 v) { return xx_rotl(acc + v * XXP2, 31) * XXP1; }
 ZG_DEV u64 xx_merge(u64 h, u64 v) { return (h ^ xx_round(0, v)) * XXP1 + XXP4; }
 
+// The accumulator recurrence acc' = rotl(acc + x, 31) * P1 (x = data * P2, off the chain) is the serial bottleneck of a
+// big input: written naively it is six dependent operations per step (64-bit add with carry, two funnel shifts, a
+// wide multiply and two cross-term multiplies).  Carrying b = acc + x instead gives b' = rotl(b, 31) * P1 + x', where
+// the addition rides on the multiply-add: funnel shift -> mad.wide (64-bit addend) -> the two cross terms = 4 levels.
+struct XxChain {
+	u32 lo, hi;  // b = acc + x of the step about to be taken
+};
+ZG_DEV void xx_chain_start(XxChain& c, u64 acc, u64 x) {
+	u64 b = acc + x;
+	c.lo = (u32)b;
+	c.hi = (u32)(b >> 32);
+}
+// one step: consumes the pending b, takes the NEXT stripe's x (or 0 for the last step) -> new b
+ZG_DEV void xx_chain_step(XxChain& c, u64 xnext) {
+	const u32 pl = (u32)XXP1, ph = (u32)(XXP1 >> 32);
+	u32 rl = __funnelshift_r(c.hi, c.lo, 1);   // rotl64(b, 31), low and high words
+	u32 rh = __funnelshift_r(c.lo, c.hi, 1);
+	u32 cross = rl * ph + rh * pl;
+#ifdef ZG_EMU
+	u64 t = (u64)rl * pl + xnext;
+#else
+	u64 t;
+	asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(rl), "r"(pl), "l"(xnext));
+#endif
+	c.lo = (u32)t;
+	c.hi = (u32)(t >> 32) + cross;
+}
+ZG_DEV u64 xx_chain_value(const XxChain& c) { return ((u64)c.hi << 32) | c.lo; }
+
 struct XxState {
 	u64 v1, v2, v3, v4;
 };
@@ -122,8 +151,13 @@ ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 			r3 = zg_ld64(qn + 24);
 		}
 		if (lane < 4) {
+			// b = acc + x0, then 32 steps each absorbing the next stripe's x (the last one absorbs 0: b becomes acc)
+			XxChain ch;
+			xx_chain_start(ch, acc, sb[lane]);
 			ZG_UNROLL
-			for (u32 i = 0; i < 32; i++) acc = xx_rotl(acc + sb[4 * i + lane], 31) * XXP1;
+			for (u32 i = 1; i < 32; i++) xx_chain_step(ch, sb[4 * i + lane]);
+			xx_chain_step(ch, 0);
+			acc = xx_chain_value(ch);
 		}
 		__syncwarp();
 	}
