@@ -94,6 +94,25 @@ def cpu_reference_run(seed: int, sample_bytes: int, level: int, cores: int):
                 value=nbytes / (tp + tu) / 1e9, pack_s=tp, unpack_s=tu)
 
 
+def _ratio_worker(args):
+    seed, total_bytes, levels, wid, nworkers = args
+    from oracle import ref_path
+
+    _, sub, files = _cpu_files("c2", seed, total_bytes, wid, nworkers)
+    return sub.total_bytes, {lv: sum(len(ref_path.ref_compress(f, level=lv)) for f in files) for lv in levels}
+
+
+def cpu_ratio_run(seed: int, sample_bytes: int, levels, cores: int):
+    """libzstd's ratio at each level on a C2 sample (the reference's call sequence), for the line's `levels` table."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ratio_worker, [(seed, sample_bytes, tuple(levels), w, cores) for w in range(cores)])
+    n = sum(r[0] for r in res)
+    return {lv: n / max(1, sum(r[1][lv] for r in res)) for lv in levels}
+
+
 def _c5_worker(args):
     """One host core of the C5 producer: frames made the reference's way (RefEncoder call sequence) at each level over
     this worker's files of the mix, and the reference's own unpack + verify of them, timed."""
@@ -509,6 +528,7 @@ def main():
     ap.add_argument("--c5-unique-gb", type=float, default=2.2, help="unique input per level the reference path compresses on the host")
     ap.add_argument("--c5-total-gb", type=float, default=50.0, help="total decoded bytes per unpack pass over the three levels (replication on device)")
     ap.add_argument("--level", type=int, default=3)
+    ap.add_argument("--levels-sample-gb", type=float, default=0.5, help="C2 sample packed at levels 1/3/9 for the ratio table")
     ap.add_argument("--cpu-sample-mb-per-core", type=float, default=96.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -524,7 +544,7 @@ def main():
     workload = workload_text(args.config, args, world, args.scaling)
     extras_on = []
     if args.extras == "auto":
-        extras_on = (["strong"] if world > 1 else []) + ["c4", "c3", "c5"] if args.config == "c2" else []
+        extras_on = (["strong"] if world > 1 else []) + ["levels", "c4", "c3", "c5"] if args.config == "c2" else []
     elif args.extras != "none":
         extras_on = [x for x in args.extras.split(",") if x]
 
@@ -565,6 +585,12 @@ def main():
         cpu = cpu_reference_run(2, sample, args.level, cores)
         cpu["sample"] = (f"{sample / 1e6:.0f} MB of the same C2 corpus, split over {cores} processes; libzstd 1.5.5 + BLAKE3 with the "
                          "reference's call sequence (oracle/ref_path.py), in memory, no file I/O")
+    ref_ratios = None
+    if rank == 0 and "levels" in extras_on:
+        try:
+            ref_ratios = cpu_ratio_run(2, int(args.levels_sample_gb * 1e9), (1, 3, 9), cores)
+        except Exception as e:
+            ref_ratios = {"error": f"{type(e).__name__}: {e}"}
     c5 = None
     c5_err = None
     if args.config == "c5" or "c5" in extras_on:
@@ -842,6 +868,21 @@ def main():
             extras[name] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
 
+    if "levels" in extras_on:
+        # ratio (and pack rate) at levels 1 / 3 / 9 next to libzstd's on the same C2 sample (north star: "the compression
+        # ratio at each level is reported next to the reference's")
+        def levels_leg():
+            sample = corpus.c2_source_tree(total_bytes=int(args.levels_sample_gb * 1e9), seed=2)
+            out = {}
+            for lv in (1, 3, 9):
+                r = leg_roundtrip(cx, sample, lv, 2, 1)
+                ref = ref_ratios.get(lv) if isinstance(ref_ratios, dict) else None
+                out[f"L{lv}"] = {"ratio": r["ratio"], "ratio_reference": ref, "ours_over_reference_size": (ref / r["ratio"]) if ref else None,
+                                 "pack_gbs": r["pack_gbs"], "unpack_gbs": r["unpack_gbs"]}
+            out["sample"] = f"{args.levels_sample_gb:g} GB of the C2 corpus (seed 2), the same files for both"
+            return out
+
+        leg("levels", levels_leg)
     if "strong" in extras_on and world > 1:
         leg("c2_strong", lambda: dict(leg_roundtrip(cx, shape("c2", "strong"), args.level, max(2, min(args.steps, 5)), 2),
                                       workload=workload_text("c2", args, world, "strong")))

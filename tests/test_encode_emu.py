@@ -182,3 +182,60 @@ def test_sliced_host_api_and_chunked_encoder_equal_one_shot(emu):
         emu.dll.zg_internal_set_slice_bytes(C.c_uint64(0))
         emu.dll.zg_internal_set_encode_chunk_bytes(C.c_uint64(0))
     assert all(x == results[0] for x in results[1:])
+
+
+def _pack_with(emu, files, level=3, params=()):
+    cctx = emu.zg_cctx_create()
+    emu.check(emu.zg_cctx_init(cctx, 0))
+    emu.check(emu.zg_cctx_set_parameter(cctx, 201, 1))
+    emu.check(emu.zg_cctx_set_parameter(cctx, 100, level))
+    for p, v in params:
+        emu.check(emu.zg_cctx_set_parameter(cctx, p, v))
+    emu.check(emu.zg_cctx_reset_archive(cctx, 12))
+    r = pack_batch(emu, cctx, files)
+    emu.zg_cctx_free(cctx)
+    assert r["rc"] == 0
+    frames = [r["frames"][o - 12 : o - 12 + l] for o, l in zip(r["off"], r["len"])]
+    for f, fr in zip(files, frames):
+        assert ref_path.ref_decompress(fr, len(f)) == f  # whatever the parameters, libzstd restores the frames
+        assert ref_path.ref_decompress_stream(bytes(fr), 0) == f
+    return sum(len(fr) for fr in frames), frames
+
+
+def test_levels_search_deeper_and_zstd_parameters_are_honoured_or_refused(emu):
+    """Levels >= 6 / >= 9 keep 2 / 4 candidates per hash set; the --zstd parameters of pack.rs:140-195 either steer the
+    match finder or are refused -- none is silently ignored."""
+    from tests.golden.recipes import text
+
+    rng = np.random.default_rng(11)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(3, 9)), dtype=np.uint8)) for _ in range(600)]
+    src = b" ".join(words[int(i)] for i in rng.zipf(1.3, 60000) % 600)
+    files = [src[:150_000], text(40_000, 3), src[150_000:230_000] + src[:20_000]]
+    size = {lv: _pack_with(emu, files, level=lv)[0] for lv in (1, 3, 6, 9)}
+    assert size[1] >= size[3] >= size[6] >= size[9] and size[9] < size[3]
+    # searchLog / strategy reach the same search depths as the levels that imply them
+    assert _pack_with(emu, files, 3, [(104, 2)])[0] == size[9]
+    assert _pack_with(emu, files, 3, [(107, 7)])[0] == size[9]
+    assert _pack_with(emu, files, 9, [(107, 1)])[0] == _pack_with(emu, files, 1)[0]  # strategy fast: greedy, one candidate
+    # minMatch: no match shorter than asked for
+    from oracle import ref_path as rp
+
+    for mm in (5, 7):
+        total, frames = _pack_with(emu, files, 3, [(105, mm)])
+        assert total > size[3]
+    # windowLog below 16: no offset beyond the window; hashLog: a smaller table finds less
+    total, frames = _pack_with(emu, files, 3, [(101, 10)])
+    assert total > size[3]
+    for fr in frames:
+        data, err, consumed, st = rp.c_zstd_decompress_frame(fr, 400_000)
+        assert err == 0 and st["window_size"] >= 0
+    assert _pack_with(emu, files, 3, [(102, 8)])[0] > size[3]
+    assert _pack_with(emu, files, 3, [(102, 20)])[0] == size[3]  # adjusted down to the largest table there is
+    # refused: what has no counterpart
+    cctx = emu.zg_cctx_create()
+    for p, v, code in ((105, 3, 40), (103, 20, 40), (106, 64, 40), (105, 9, 42), (107, 12, 42), (101, 40, 42)):
+        r = emu.zg_cctx_set_parameter(cctx, p, v)
+        assert emu.zg_is_error(r) and emu.zg_get_error_code(r) == code, (p, v)
+    for p in (103, 106):
+        assert emu.zg_cctx_set_parameter(cctx, p, 0) == 0  # "not set" is fine
+    emu.zg_cctx_free(cctx)

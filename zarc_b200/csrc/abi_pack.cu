@@ -213,6 +213,9 @@ static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64
 		ZG_TRY(zg_pk_build_ulist(s, first, c->uidx.as<u64>(), c->blkfirst.as<u64>(), F, c->ulist.as<u32>(), c->blk_base.as<u64>(), nuniq,
 		                         nblocks));
 		// (3) compress every new content (content_frame.rs:41 -> lowlevel_frames.rs:30)
+		const ZgCParams cparams = {c->level, c->other_params[ZG_c_windowLog - 100], c->other_params[ZG_c_hashLog - 100],
+		                           c->other_params[ZG_c_searchLog - 100], c->other_params[ZG_c_minMatch - 100],
+		                           c->other_params[ZG_c_strategy - 100]};
 		bool side = false;
 		if (c->checksum) {
 			// the checksums only need the input and the unique list: fork them onto a side stream (launched first, higher
@@ -234,7 +237,7 @@ static size_t pack_core_body(zg_cctx* c, ZgArchive& A, const u8* blob, const u64
 			}
 		}
 		ZG_TRY(zg_zstd_encode_run(s, c->ze, blob, off, c->comp_off.as<u64>(), len, c->ulist.as<u32>(), c->blk_base.as<u64>(), (u32)nuniq,
-		                          nblocks, comp_bytes, c->comp.as<u8>(), c->blk_csize.as<u32>(), c->level));
+		                          nblocks, comp_bytes, c->comp.as<u8>(), c->blk_csize.as<u32>(), cparams));
 		if (c->checksum && !side) ZG_TRY(zg_pk_xxh64_list(s, blob, off, len, c->ulist.as<u32>(), nuniq, c->xxh.as<u64>()));
 		if (side) ZG_CUDA(cudaStreamWaitEvent(s, c->xx_join, 0));
 		// (4) frame lengths -> archive offsets (content_frame.rs:22,45)
@@ -340,16 +343,30 @@ size_t zg_cctx_set_parameter(zg_cctx* c, int param, int value) {
 		if (value != 0 && (value < 10 || value > 31)) return ZG_ERR(ZG_error_parameter_outOfBound);
 		c->other_params[param - 100] = value;
 		return (size_t)value;
+	// the --zstd parameters (pack.rs:140-195), with libzstd's bounds; how each one steers the GPU match finder is in
+	// ze_resolve_params (zstd_encode.cu).  A parameter that cannot be honoured is refused, never silently ignored.
 	case ZG_c_hashLog:
-	case ZG_c_chainLog:
+		if (value != 0 && (value < 6 || value > 30)) return ZG_ERR(ZG_error_parameter_outOfBound);
+		c->other_params[param - 100] = value;  // tables above 2^12 positions do not exist here: adjusted down, as libzstd adjusts cparams to the input
+		return (size_t)value;
 	case ZG_c_searchLog:
-	case ZG_c_minMatch:
-	case ZG_c_targetLength:
-	case ZG_c_strategy:
-		// accepted for CLI compatibility (pack.rs:140-195); the GPU match finder has its own tuning
-		if (value < 0) return ZG_ERR(ZG_error_parameter_outOfBound);
+		if (value != 0 && (value < 1 || value > 30)) return ZG_ERR(ZG_error_parameter_outOfBound);
 		c->other_params[param - 100] = value;
 		return (size_t)value;
+	case ZG_c_minMatch:
+		if (value != 0 && (value < 3 || value > 7)) return ZG_ERR(ZG_error_parameter_outOfBound);
+		if (value == 3) return ZG_ERR(ZG_error_parameter_unsupported);  // the 4-byte hash cannot find 3-byte matches
+		c->other_params[param - 100] = value;
+		return (size_t)value;
+	case ZG_c_strategy:
+		if (value != 0 && (value < 1 || value > 9)) return ZG_ERR(ZG_error_parameter_outOfBound);
+		c->other_params[param - 100] = value;
+		return (size_t)value;
+	case ZG_c_chainLog:
+	case ZG_c_targetLength:
+		// no chain table and no optimal parser here: only the "not set" value is accepted
+		if (value != 0) return ZG_ERR(ZG_error_parameter_unsupported);
+		return 0;
 	default:
 		return ZG_ERR(ZG_error_parameter_unsupported);
 	}

@@ -141,9 +141,12 @@ struct ZgZeWork {
 		for (ZgBuf* b : {&queue, &meta, &seqbuf, &litbuf, &codebuf, &stbbuf, &bounds, &bins, &order, &info}) b->release();
 	}
 };
+struct ZgCParams {  // the cctx's compression parameters (0 = not set), libzstd's names
+	int level, window_log, hash_log, search_log, min_match, strategy;
+};
 size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
                           const u32* ulist, const u64* blk_base, u32 nuniq, u64 nblocks, u64 comp_bytes, u8* comp, u32* blk_csize,
-                          int level);
+                          const ZgCParams& cparams);
 
 // ---- per-kernel device timing (abi.cu): CUDA events on the launching stream, off by default ----
 enum {

@@ -125,6 +125,7 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 // from there: the chain's arithmetic latency is all that is left (~2 GB/s per input; many inputs run
 // side by side).  `sb`: 128 u64 of shared memory per warp.  All lanes call; all lanes get the hash.
 #define XX_WARP_MIN 8192u
+#define XX_PREFETCH_CHUNKS 16u
 ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 	u32 lane = zg_lane();
 	u64 acc = lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;  // seed 0
@@ -138,6 +139,9 @@ ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 		r3 = zg_ld64(q + 24);
 	}
 	for (u64 c = 0; c < chunks; c++) {
+		// a warp has one chunk in flight: without help it would stream at one DRAM latency per KiB (measured 1.3 GB/s on a
+		// 4 GiB input).  The lines 16 KiB ahead are asked into L2 now, so that the loads below find them there.
+		if (c + XX_PREFETCH_CHUNKS < chunks) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << 10));
 		sb[4 * lane + 0] = r0 * XXP2;  // the products are off the chain: all 32 lanes make them
 		sb[4 * lane + 1] = r1 * XXP2;
 		sb[4 * lane + 2] = r2 * XXP2;

@@ -774,6 +774,15 @@ ZG_DEV_NOINLINE u32 ze_seq_table(ZeWarp* W, const ZeCT& predef, u32 t, const u32
 // histogramming them -- is then done lane-parallel from the selection mask.
 ZG_DEV u32 ze_hash4(u32 v, u32 hlog) { return (v * 2654435761u) >> (32 - hlog); }
 
+// what the level and the --zstd parameters (pack.rs:140-195) resolve to, see ze_resolve_params
+struct ZeParams {
+	u32 lazy;       // 1: one-step lazy parse (levels >= 3 / strategies greedy and up)
+	u32 ways;       // candidates kept per hash set: 1 (levels < 6), 2 (6-8), 4 (>= 9); searchLog
+	u32 min_match;  // shortest match emitted (4..7); minMatch
+	u32 max_dist;   // largest offset searched (<= 65535: matches never leave the 64 KiB the 16-bit table reaches); windowLog
+	u32 hlog_cap;   // hash table log2 (8..12); hashLog
+};
+
 // 16 bytes at an arbitrary address as four words.  Only aligned words are touched, and words that
 // start at or beyond `lim` read as zero (nothing past the block is dereferenced).
 ZG_DEV void ze_ld128(const u8* p, const u8* lim, u32 out[4]) {
@@ -811,11 +820,43 @@ ZG_DEV u32 ze_eq16(const u32 a[4], const u32 b[4]) {
 	return 16u;
 }
 
-ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 n, u32 lazy, u32* lit_count) {
+// One more candidate for the position `pos` (deeper searches, WAYS > 1): a 4-byte check first, then the same 16 bytes per
+// round trip verification as the single-candidate path; kept when longer than what the lane has.
+ZG_DEV void ze_try_candidate(const u8* src, const u8* lim, u32 n, u32 pos, i32 cand, u32 v, const u32 own[4], u32 own_before, u32& mlen,
+                             u32& moff, u32& bmatch) {
+	if (cand < 0) return;
+	if (zg_ld32(src + cand) != v) return;
+	u32 c[4];
+	u32 cand_before = ze_ld128_prev<true>(src + cand, src, lim, c);
+	u32 maxl = zg_min<u32>(n - pos, ZE_LANE_CAP);
+	u32 l = ze_eq16(own, c);
+	while (l < maxl && (l & 15u) == 0) {
+		u32 a[4];
+		ze_ld128(src + pos + l, lim, a);
+		ze_ld128(src + (u32)cand + l, lim, c);
+		u32 e = ze_eq16(a, c);
+		l += e;
+		if (e < 16) break;
+	}
+	l = zg_min<u32>(l, maxl);
+	if (l > mlen) {
+		mlen = l;
+		moff = pos - (u32)cand;
+		bmatch = cand >= 4 ? (u32)__clz((int)(own_before ^ cand_before)) >> 3 : 0u;
+	}
+}
+
+// WAYS = 1: one 16-bit position per hash (levels < 6).  WAYS = 2 / 4: the table is 2^hlog / WAYS sets of WAYS positions,
+// most recent first; every position verifies all of them (and the nearest same-set position of its own window) and keeps
+// the longest match -- the deeper search of the higher levels (libzstd: chain searches of 2^searchLog attempts).
+template <int WAYS>
+ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 n, const ZeParams& prm, u32* lit_count) {
 	u32 lane = zg_lane();
 	u32 ltmask = zg_lanemask_lt();
+	const u32 lazy = prm.lazy, minmatch = prm.min_match, maxdist = prm.max_dist;
+	constexpr u32 LW = WAYS == 4 ? 2 : WAYS == 2 ? 1 : 0;
 	u32 hlog = 8;
-	while (hlog < ZE_HLOG_MAX && (1u << hlog) < n) hlog++;
+	while (hlog < prm.hlog_cap && (1u << hlog) < n) hlog++;
 	u16* htab = W->htab;
 	const u8* lim = src + n;
 	{
@@ -836,6 +877,8 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 		u32 own_before = inner ? ze_ld128_prev<false>(src + pos, src, lim, own)
 		                       : ze_ld128_prev<true>(src + pos, src, lim, own);  // + the four bytes before this position
 		u32 v = own[0];
+		u32 mlen = 0, bmatch = 0, moff = 0;
+		if (WAYS == 1) {
 		u32 h = valid ? ze_hash4(v, hlog) : (0x80000000u | lane);
 		u32 te = valid ? htab[h] : 0;
 		u32 peers = __match_any_sync(ZG_FULL, h);
@@ -852,9 +895,9 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 				if (c >= (i32)pos) c -= 65536;
 				cand = c;
 			}
+			if (cand >= 0 && pos - (u32)cand > maxdist) cand = -1;
 		}
 		// verify + extend, 16 bytes per memory round trip (both sides loaded before any compare)
-		u32 mlen = 0, bmatch = 0;
 		if (cand >= 0) {
 			u32 c[4];
 			u32 cand_before = inner ? ze_ld128_prev<false>(src + cand, src, lim, c) : ze_ld128_prev<true>(src + cand, src, lim, c);
@@ -874,7 +917,44 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 				if (cand >= 4) bmatch = (u32)__clz((int)(own_before ^ cand_before)) >> 3;
 			}
 		}
-		u32 moff = mlen ? pos - (u32)cand : 0;
+		moff = mlen ? pos - (u32)cand : 0;
+		} else {
+			// ---- set-associative table ----
+			u32 set = valid ? ze_hash4(v, hlog - LW) : (0x80000000u | lane);
+			u64 e = 0;
+			if (valid) e = WAYS == 4 ? ((const u64*)htab)[set] : (u64)((const u32*)htab)[set];
+			u32 peers = __match_any_sync(ZG_FULL, set);
+			__syncwarp();
+			if (valid && (peers >> lane) == 1u) {
+				// the set's leader (its highest lane) puts the set's positions of this window in front, most recent first
+				u64 ne = e;
+				u32 m = peers;
+				u32 cnt = zg_min<u32>((u32)__popc(m), (u32)WAYS);
+				ne = cnt >= (u32)WAYS ? 0ull : ne << (16 * cnt);
+				ZG_UNROLL
+				for (int k = 0; k < WAYS; k++) {
+					if (m) {
+						u32 l = 31u - (u32)__clz((int)m);
+						m &= ~(1u << l);
+						ne |= (u64)((ip + l) & 0xffffu) << (16 * k);
+					}
+				}
+				if (WAYS == 4) ((u64*)htab)[set] = ne;
+				else ((u32*)htab)[set] = (u32)ne;
+			}
+			if (valid && pos >= mend) {
+				u32 lower = peers & ltmask;
+				if (lower) ze_try_candidate(src, lim, n, pos, (i32)(ip + (31u - (u32)__clz((int)lower))), v, own, own_before, mlen, moff, bmatch);
+				ZG_UNROLL
+				for (int k = 0; k < WAYS; k++) {
+					u32 te = (u32)(e >> (16 * k)) & 0xffffu;
+					i32 c = (i32)((pos & ~0xffffu) | te);
+					if (c >= (i32)pos) c -= 65536;
+					// (an empty slot reads as position 0, like the one-way table: a candidate like any other)
+					if (c >= 0 && pos - (u32)c <= maxdist) ze_try_candidate(src, lim, n, pos, c, v, own, own_before, mlen, moff, bmatch);
+				}
+			}
+		}
 		__syncwarp();
 		// ---- selection ----
 		// Greedy with one-step lazy evaluation, resolved without a per-candidate loop: a match is
@@ -884,9 +964,9 @@ ZG_DEV u32 ze_match_block(ZeMatchWarp* W, u64* seq, u8* lit, const u8* src, u32 
 		// it is taken (first good lane at or after its match end), and the warp only chases that
 		// chain from the first good lane.  A selected match is maximal for its offset, so the next
 		// one can never be "zero literals + same offset" (ze_assign_repcodes double-checks).
-		u32 has = __ballot_sync(ZG_FULL, mlen >= ZE_MINMATCH);
+		u32 has = __ballot_sync(ZG_FULL, mlen >= minmatch);
 		u32 mlen_up = __shfl_down_sync(ZG_FULL, mlen, 1);
-		bool skip = lazy && lane < 31 && mlen >= ZE_MINMATCH && mlen_up > mlen + 1;
+		bool skip = lazy && lane < 31 && mlen >= minmatch && mlen_up > mlen + 1;
 		u32 good = has & ~__ballot_sync(ZG_FULL, skip);
 		u32 t = lane + mlen;
 		u32 nxt = t < 32 ? (u32)__ffs((int)(good & ~((1u << t) - 1u))) - 1u : 0xffffffffu;
@@ -1432,10 +1512,6 @@ ZG_DEV u32 ze_sequences_pack(ZeWarp* W, const u64* seq, const u32* codes, const 
 	return pk.ovf ? 0 : bytes;
 }
 
-struct ZeParams {
-	u32 lazy;      // 1: one-step lazy parse (levels >= 3)
-	u32 window;    // reserved
-};
 struct ZeBlk {
 	u32 f;         // file
 	u32 n;         // block bytes
@@ -1547,6 +1623,7 @@ __global__ void __launch_bounds__(256) k_ze_order_scatter(ZeJob J, u32 nchunks, 
 }
 
 // K2
+template <int WAYS>
 __global__ void __launch_bounds__(ZE_WARPS * 32, ZE_MIN_CTAS) k_zstd_match_blocks(ZeJob J, u32 chunk, u32* queue, ZeParams prm) {
 	ZG_DYN_SMEM(ZeMatchWarp, sm);
 	ZeMatchWarp* W = &sm[threadIdx.x >> 5];
@@ -1559,7 +1636,7 @@ __global__ void __launch_bounds__(ZE_WARPS * 32, ZE_MIN_CTAS) k_zstd_match_block
 		u8* lit = J.litbuf + rel;
 		u32 nseq = ZE_RAW, nlit = 0;
 		if (B.n >= 16) {
-			nseq = ze_match_block(W, seq, lit, J.blob + J.file_off[B.f] + B.j * ZS_BLOCK_MAX, B.n, prm.lazy, &nlit);
+			nseq = ze_match_block<WAYS>(W, seq, lit, J.blob + J.file_off[B.f] + B.j * ZS_BLOCK_MAX, B.n, prm, &nlit);
 			__syncwarp();
 			// later blocks of a frame are encoded independently of their predecessors: unknown history
 			if (!ze_assign_repcodes(W, seq, nseq, B.j == 0)) nseq = ZE_RAW;
@@ -1635,9 +1712,33 @@ __global__ void __launch_bounds__(ZE_WARPS * 32, ZE_ENT_CTAS) k_zstd_sequences(Z
 static u64 g_ze_chunk_bytes = ZE_CHUNK_BYTES;
 extern "C" void zg_internal_set_encode_chunk_bytes(u64 v) { g_ze_chunk_bytes = v ? (v + 15) & ~(u64)15 : ZE_CHUNK_BYTES; }
 
+// The compression level and the advanced parameters of the CLI's --zstd option (pack.rs:140-195; libzstd's
+// ZSTD_cParameter numbers) as this match finder honours them.  Level -> strategy follows libzstd's table in spirit:
+// levels 1-2 (fast, dfast) parse greedily, 3-5 add one-step lazy evaluation, 6-8 search two candidates per position,
+// 9 and up four.  An explicit strategy / searchLog / hashLog / minMatch / windowLog overrides what the level implies:
+//   strategy   1-2 greedy, 3-5 lazy, 6-9 lazy + 4 candidates          searchLog  candidates = 2^min(searchLog, 2)
+//   hashLog    table of 2^clamp(hashLog, 8, 12) positions             minMatch   4..7 (3 is refused by zg_cctx_set_parameter)
+//   windowLog  matches no further back than min(2^windowLog, 65535)
+// chainLog and targetLength have no counterpart here and are refused when set (zg_cctx_set_parameter).
+static ZeParams ze_resolve_params(const ZgCParams& cp) {
+	ZeParams p;
+	int level = cp.level;
+	p.lazy = level >= 3 ? 1 : 0;
+	p.ways = level >= 9 ? 4 : level >= 6 ? 2 : 1;
+	if (cp.strategy > 0) {
+		p.lazy = cp.strategy >= 3 ? 1 : 0;
+		p.ways = cp.strategy >= 6 ? 4 : 1;
+	}
+	if (cp.search_log > 0) p.ways = cp.search_log >= 2 ? 4 : 2;
+	p.min_match = cp.min_match >= 4 ? (u32)zg_min<int>(cp.min_match, 7) : ZE_MINMATCH;
+	p.max_dist = cp.window_log > 0 && cp.window_log < 16 ? (1u << cp.window_log) : 65535u;
+	p.hlog_cap = cp.hash_log > 0 ? (u32)zg_max<int>(8, zg_min<int>(cp.hash_log, ZE_HLOG_MAX)) : (u32)ZE_HLOG_MAX;
+	return p;
+}
+
 size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64* file_off, const u64* comp_off, const u64* file_len,
                           const u32* ulist, const u64* blk_base, u32 nuniq, u64 nblocks, u64 comp_bytes, u8* comp, u32* blk_csize,
-                          int level) {
+                          const ZgCParams& cparams) {
 	if (nblocks == 0) return 0;
 	const u64 chunk_bytes = g_ze_chunk_bytes;
 	u32 nchunks = (u32)((comp_bytes + chunk_bytes - 1) / chunk_bytes);
@@ -1654,9 +1755,7 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	if (sorted && (w.bins.reserve((size_t)nchunks * ZE_OBINS * 4) || w.order.reserve(nblocks * 4) || w.info.reserve(nblocks * sizeof(ZeBlk))))
 		return ZG_ERR(ZG_error_memory_allocation);
 	cudaMemsetAsync(w.queue.p, 0, qbytes, s);
-	ZeParams prm;
-	prm.lazy = level >= 3 ? 1 : 0;
-	prm.window = 0;
+	const ZeParams prm = ze_resolve_params(cparams);
 	ZeJob J;
 	J.blob = blob;
 	J.file_off = file_off;
@@ -1683,7 +1782,9 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	static ZgPerDevice attr_dev;
 	bool& attr_set = *attr_dev.slot();
 	if (!attr_set) {
-		if (cudaFuncSetAttribute(k_zstd_match_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess ||
+		if (cudaFuncSetAttribute(k_zstd_match_blocks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess ||
+		    cudaFuncSetAttribute(k_zstd_match_blocks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess ||
+		    cudaFuncSetAttribute(k_zstd_match_blocks<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m) != cudaSuccess ||
 		    cudaFuncSetAttribute(k_zstd_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l) != cudaSuccess ||
 		    cudaFuncSetAttribute(k_zstd_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q) != cudaSuccess)
 			return ZG_ERR(ZG_error_device);
@@ -1706,7 +1807,9 @@ size_t zg_zstd_encode_run(cudaStream_t s, ZgZeWork& w, const u8* blob, const u64
 	for (u32 k = 0; k < nchunks; k++) {
 		u32* qk = q + (size_t)k * ZE_NQ;
 		zg_prof_begin(ZG_K_MATCH, s);
-		ZG_LAUNCH(k_zstd_match_blocks, grid_m, ZE_WARPS * 32, smem_m, s, J, k, qk + 0, prm);
+		if (prm.ways == 4) ZG_LAUNCH(k_zstd_match_blocks<4>, grid_m, ZE_WARPS * 32, smem_m, s, J, k, qk + 0, prm);
+		else if (prm.ways == 2) ZG_LAUNCH(k_zstd_match_blocks<2>, grid_m, ZE_WARPS * 32, smem_m, s, J, k, qk + 0, prm);
+		else ZG_LAUNCH(k_zstd_match_blocks<1>, grid_m, ZE_WARPS * 32, smem_m, s, J, k, qk + 0, prm);
 		zg_prof_end(ZG_K_MATCH, s);
 		zg_prof_begin(ZG_K_LITERALS, s);
 		ZG_LAUNCH(k_zstd_literals, grid_e, ZE_WARPS * 32, smem_l, s, J, k, qk + 1);
