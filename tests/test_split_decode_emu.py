@@ -96,6 +96,44 @@ def test_chunked_staging_equals_one_pass(emu):
         emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(0))
 
 
+def _window_edge_files():
+    """What stresses the chain executor's shared-memory window: matches longer than the window (periods of 70 000 and
+    200 000 bytes), matches that overlap themselves across a slide (period 37), sources far behind the window, stored
+    blocks in the middle of a chain, and a long tail of literals."""
+    rng = np.random.default_rng(99)
+    a = rand(70_000, 1)
+    b = rand(200_000, 2)
+    return [a * 5 + text(30_000, 3),
+            b + b + text(150_000, 4) + b[:150_000],
+            text(20_000, 5) + rand(37, 6) * 9000 + text(100_000, 5),
+            text(300_000, 7) + rand(140_000, 8) + text(300_000, 7),
+            text(180_000, 9) + bytes(rng.integers(0, 256, 131_000, dtype=np.uint8)),
+            (text(5000, 10) + bytes(3000)) * 60]
+
+
+def test_chain_executor_window_edges_and_both_modes(emu):
+    files = _window_edge_files()
+    try:
+        for mode in (2, 0):  # 2: always the chain executor, 0: per-block flags
+            emu.dll.zg_internal_set_decode_chain_mode(C.c_uint32(mode))
+            for level in (1, 3):
+                frames = [ref_path.ref_compress(f, level=level) for f in files]
+                outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], [_b3(f) for f in files])
+                assert rc == 0 and status == [0] * len(files)
+                assert outs == files and ok == [1] * len(files)
+                ex = _stats_ex(emu)
+                assert ex[5] > 0 and (ex[7] > 0) == (mode == 2)
+        # small chunks: the window starts over at every chunk boundary
+        emu.dll.zg_internal_set_decode_chain_mode(C.c_uint32(2))
+        emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(5))
+        frames = [ref_path.ref_compress(f, level=3) for f in files]
+        outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], [_b3(f) for f in files])
+        assert rc == 0 and outs == files and ok == [1] * len(files)
+    finally:
+        emu.dll.zg_internal_set_decode_chain_mode(C.c_uint32(1))
+        emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(0))
+
+
 def test_split_threshold_and_mixed_batch(emu):
     files = _files()
     own = _own_frames(emu, files)

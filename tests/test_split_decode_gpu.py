@@ -28,3 +28,7 @@ def test_short_blocks_are_not_mistaken_for_full_ones(gpu):
 
 def test_corruption_inside_split_frames(gpu):
     cases.test_corruption_inside_split_frames(gpu)
+
+
+def test_chain_executor_window_edges_and_both_modes(gpu):
+    cases.test_chain_executor_window_edges_and_both_modes(gpu)

@@ -93,12 +93,13 @@ cudaError_t zg_publish(cudaStream_t s, const void* dev_src, void* pinned_dst, u3
 struct ZgZdStaged {  // the staged pipeline for multi-block frames (zstd_decode_staged.cu)
 	ZgBuf nblk, first, multi, single, tot, hist;                 // per frame: block count, first block; frame lists; totals; histogram
 	ZgBuf blk, res, out_pos, rep_in, dep, done;                  // per block
-	ZgBuf tail, f_out, f_rep, f_status, done_upto;               // per frame: running state across chunks
+	ZgBuf tail, f_out, f_rep, f_status, done_upto, f_chain;      // per frame: running state across chunks
+	ZgBuf item_of, chain_list;                                   // per block: its item in the chunk; frames for the chain executor
 	ZgBuf jbase, cursor, queue, items, seq_cnt, lit_cnt, seq_off, lit_off, seq_stage, lit_stage, tabs;  // per chunk
 	ZgHostBuf hh;
 	void release() {
 		for (ZgBuf* b : {&nblk, &first, &multi, &single, &tot, &hist, &blk, &res, &out_pos, &rep_in, &dep, &done, &tail, &f_out, &f_rep, &f_status,
-		                 &done_upto, &jbase, &cursor, &queue, &items, &seq_cnt, &lit_cnt, &seq_off, &lit_off, &seq_stage, &lit_stage, &tabs})
+		                 &done_upto, &f_chain, &item_of, &chain_list, &jbase, &cursor, &queue, &items, &seq_cnt, &lit_cnt, &seq_off, &lit_off, &seq_stage, &lit_stage, &tabs})
 			b->release();
 		hh.release();
 	}

@@ -802,8 +802,21 @@ ZG_DEV void zd_lane_overlap(u8* d, u32 off, u32 ml) {
 // written (match starts and ends grow with the lane, so that set is a range of lanes, found by two binary
 // searches over shuffles); all ready matches of a wave copy lane-parallel.  A row of n sequences takes (dependency depth) waves, not n
 // steps, and every wave is a few 16-byte round trips.
+// Where a row's bytes live.  ZdDirect: the frame's output in global memory (CG: match sources are read through L2, for
+// bytes another SM may have written during the kernel).  ZdWindow (zstd_decode_staged.cu, the chain executor): the recent
+// output in a shared-memory window, older bytes in global memory.
 template <bool CG>
-ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, u8* out, u64& o_io, u64 base, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte,
+struct ZdDirect {
+	u8* out;
+	ZG_DEV u8* dst(u64 pos) const { return out + pos; }
+	ZG_DEV void lane_copy(u64 dpos, u64 spos, u32 n) const { zd_lane_copy<CG>(out + dpos, out + spos, n); }
+	ZG_DEV void lane_overlap(u64 dpos, u32 off, u32 ml) const { zd_lane_overlap<CG>(out + dpos, off, ml); }
+	ZG_DEV void warp_copy(u64 dpos, u64 spos, u32 n) const { zg_warp_copy_t<CG>(out + dpos, out + spos, n); }
+	ZG_DEV void warp_match(u64 dpos, u32 off, u32 ml) const { zd_warp_match<CG>(out + dpos, off, ml); }
+};
+
+template <class POL>
+ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, const POL& P, u64& o_io, u64 base, u64 cap, const u8* lit, bool lit_rle, u32 rle_byte,
                        u32 regen, u32& lpos_io) {
 	u32 lane = zg_lane();
 	u64 o = o_io;
@@ -818,8 +831,7 @@ ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, u8* out, u64& o_io, u64 base, u64 c
 	u32 rstart = incl - ml;          // my match's start relative to the row's output start
 	u64 mstart = o + rstart;         // ... and in the frame output
 	if (__any_sync(ZG_FULL, act && (u64)of > mstart - base)) return ZS_E_CORRUPT;
-	u8* md = out + mstart;
-	u8* d = md - ll;
+	u8* d = P.dst(mstart - ll);
 	u32 lsrc = lpos + (lincl - ll);
 	// (a) literals
 	u32 longl = __ballot_sync(ZG_FULL, ll > ZD_LANE_COPY_MAX);
@@ -867,16 +879,16 @@ ZG_DEV u32 zd_exec_row(u64 sq_lane, u32 cnt, u8* out, u64& o_io, u64 base, u64 c
 		u32 rdy = __ballot_sync(ZG_FULL, ready);
 		u32 longm = __ballot_sync(ZG_FULL, ready && !shortm);
 		if (ready && shortm) {
-			if (of >= ml) zd_lane_copy<CG>(md, md - of, ml);
-			else zd_lane_overlap<CG>(md, of, ml);
+			if (of >= ml) P.lane_copy(mstart, mstart - of, ml);
+			else P.lane_overlap(mstart, of, ml);
 		}
 		while (longm) {
 			int l = __ffs((int)longm) - 1;
 			longm &= longm - 1;
 			u32 n2 = __shfl_sync(ZG_FULL, ml, l), o2 = __shfl_sync(ZG_FULL, of, l);
-			u64 d2 = __shfl_sync(ZG_FULL, (u64)(uintptr_t)md, l);
-			if (o2 >= n2) zg_warp_copy_t<CG>((u8*)(uintptr_t)d2, (const u8*)(uintptr_t)d2 - o2, n2);
-			else zd_warp_match<CG>((u8*)(uintptr_t)d2, o2, n2);
+			u64 m2 = __shfl_sync(ZG_FULL, mstart, l);
+			if (o2 >= n2) P.warp_copy(m2, m2 - o2, n2);
+			else P.warp_match(m2, o2, n2);
 		}
 		__syncwarp();
 		pending &= ~rdy;
@@ -901,7 +913,7 @@ ZG_DEV void zd_exec_block(ZdWarp* W, ZdLane& U, const u64* seqs, u8* litbuf, u8*
 	u64 sq = lane < U.nseq ? seqs[lane] : 0;
 	for (u32 s0 = 0; s0 < U.nseq; s0 += 32) {
 		u64 sq_next = s0 + 32 + lane < U.nseq ? seqs[s0 + 32 + lane] : 0;  // the next row's records come in while this row executes
-		r = zd_exec_row<false>(sq, zg_min<u32>(32u, U.nseq - s0), U.out, o, U.base, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
+		r = zd_exec_row(sq, zg_min<u32>(32u, U.nseq - s0), ZdDirect<false>{U.out}, o, U.base, U.cap, lit, lit_rle, rle_byte, h.regen, lpos);
 		if (r) return zd_fail(U, r);
 		sq = sq_next;
 	}

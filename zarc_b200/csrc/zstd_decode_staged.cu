@@ -245,7 +245,7 @@ k_zds_sources(const u32* __restrict__ multi, u64 nmulti, const u64* __restrict__
 __global__ void __launch_bounds__(128)
 k_zds_chunk_items(const u32* __restrict__ multi, u64 nmulti, const u64* __restrict__ first, const u32* __restrict__ nblk,
                   const ZdsBlk* __restrict__ blk, u32 J, u32 w, const u32* __restrict__ jbase, u32* __restrict__ cursor, u32* __restrict__ items,
-                  u64* __restrict__ seq_cnt, u64* __restrict__ lit_cnt) {
+                  u32* __restrict__ item_of, u64* __restrict__ seq_cnt, u64* __restrict__ lit_cnt) {
 	u64 m = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if (m >= nmulti) return;
 	u32 k = multi[m];
@@ -257,6 +257,7 @@ k_zds_chunk_items(const u32* __restrict__ multi, u64 nmulti, const u64* __restri
 		u32 pos = jbase[j] + atomicAdd(&cursor[j], 1u);
 		u64 g = f0 + j;
 		items[pos] = (u32)g;
+		item_of[g] = pos;
 		u32 info = blk[g].info;
 		seq_cnt[pos] = blk[g].nseq;
 		lit_cnt[pos] = ((info & ZDS_I_LTYPE) >= 2 && !(info & ZDS_I_BAD)) ? (u64)((blk[g].lit_regen + 15u) & ~15u) : 0ull;
@@ -455,6 +456,8 @@ struct ZdsJob {
 	u32* done;            // per block: executed
 	u32* done_upto;       // per frame: all blocks below this index are executed (a hint that only grows)
 	u32* f_status;        // per frame: first error
+	u32* f_chain;         // per frame: a block of this chunk reads earlier blocks (the frame goes to the chain executor)
+	u32* item_of;         // per block: its position among the chunk's items
 };
 
 __global__ void __launch_bounds__(ZDS_WARPS * 32, ZDS_ENT_CTAS)
@@ -607,7 +610,7 @@ k_zds_entropy(ZdsJob J, u32* tabs, u32* queue, u32 want) {
 //    and which earlier block each block has to wait for.
 __global__ void __launch_bounds__(128)
 k_zds_frame_scan(ZdsJob J, const u32* __restrict__ multi, u64 nmulti, const u64* __restrict__ first, const u32* __restrict__ nblk, u32 J0, u32 w,
-                 u64* __restrict__ f_out, u32* __restrict__ f_rep) {
+                 u64* __restrict__ f_out, u32* __restrict__ f_rep, u32* __restrict__ chain_list, unsigned long long* chain_count) {
 	u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (m >= nmulti) return;
 	u32 k = multi[m];
@@ -618,6 +621,7 @@ k_zds_frame_scan(ZdsJob J, const u32* __restrict__ multi, u64 nmulti, const u64*
 	u64 o = f_out[k], cap = J.ulen[k];
 	u32 r0 = f_rep[3 * (u64)k], r1 = f_rep[3 * (u64)k + 1], r2 = f_rep[3 * (u64)k + 2];
 	u32 st = J.f_status[k];
+	bool chained = false;
 	for (u32 j = J0; j < hi; j++) {
 		u64 g = f0 + j;
 		ZdsRes R = J.res[g];
@@ -643,6 +647,7 @@ k_zds_frame_scan(ZdsJob J, const u32* __restrict__ multi, u64 nmulti, const u64*
 			dj = lo;
 		}
 		J.dep[g] = dj;
+		chained = chained || dj < j;
 		if (st == ZS_OK) {
 			u32 n0 = zds_resolve(R.rep[0], r0, r1, r2), n1 = zds_resolve(R.rep[1], r0, r1, r2), n2 = zds_resolve(R.rep[2], r0, r1, r2);
 			r0 = n0;
@@ -656,6 +661,8 @@ k_zds_frame_scan(ZdsJob J, const u32* __restrict__ multi, u64 nmulti, const u64*
 	f_rep[3 * (u64)k + 1] = r1;
 	f_rep[3 * (u64)k + 2] = r2;
 	J.f_status[k] = st;
+	J.f_chain[k] = chained ? 1u : 0u;
+	if (chained && st == ZS_OK) chain_list[atomicAdd(chain_count, 1ull)] = k;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -698,7 +705,7 @@ ZG_DEV void zds_wait(const u32* done, u32* done_upto, u64 f0, u32 k, u32 dj, u32
 // Phase C of one block: zd_exec_row with the symbolic offsets made concrete first, and with L2 (CG) loads for the match
 // sources, which other SMs may have written during this kernel.
 __global__ void __launch_bounds__(ZDS_WARPS * 32, ZDS_EXEC_CTAS)
-k_zds_exec(ZdsJob J, const u64* __restrict__ first, u32* queue) {
+k_zds_exec(ZdsJob J, const u64* __restrict__ first, u32* queue, u32 skip_chained) {
 	u32 lane = threadIdx.x & 31;
 	for (;;) {
 		u32 i = 0;
@@ -710,6 +717,7 @@ k_zds_exec(ZdsJob J, const u64* __restrict__ first, u32* queue) {
 		ZdsRes R = J.res[g];
 		u32 k = B.k, j = B.j;
 		u64 f0 = first[k];
+		if (skip_chained && J.f_chain[k]) continue;  // the chain executor's (nothing in this chunk waits on its flags)
 		u32 st = zds_ld_flag_warp(&J.f_status[k]);
 		if (st == ZS_OK && R.status == ZS_OK) {
 			u32 dj = J.dep[g];
@@ -742,7 +750,7 @@ k_zds_exec(ZdsJob J, const u64* __restrict__ first, u32* queue) {
 					if (__any_sync(ZG_FULL, act && rof == 0)) err = ZS_E_CORRUPT;
 					else {
 						sq = (sq & ~(u64)ZD_OFF_MAX) | rof;
-						err = zd_exec_row<true>(sq, zg_min<u32>(32u, nseq - s0), out, o, 0, cap, lit, lit_rle, rle_byte, h.regen, lpos);
+						err = zd_exec_row(sq, zg_min<u32>(32u, nseq - s0), ZdDirect<true>{out}, o, 0, cap, lit, lit_rle, rle_byte, h.regen, lpos);
 					}
 					sq = sq_next;
 				}
@@ -760,6 +768,191 @@ k_zds_exec(ZdsJob J, const u64* __restrict__ first, u32* queue) {
 		__syncwarp();
 		__threadfence();  // release: this block's bytes before its flag
 		if (lane == 0) *(volatile u32*)&J.done[g] = 1u;
+	}
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 6b. the chain executor.  A frame whose blocks read earlier blocks is a chain: every match may need bytes the matches just
+// before it produced, and through global memory each such hop costs an L2 round trip (~700 cycles store-to-load; measured
+// 100 MB/s per frame).  Here ONE warp walks the frame's blocks in order and keeps the recent output in a SHARED-MEMORY
+// WINDOW: sequence execution happens in shared memory (a hop is a shared-memory round trip), the window is written to the
+// frame's place in global memory with coalesced 16-byte stores when it slides, and only matches that reach back beyond the
+// window read global memory (old bytes, off the critical path).
+#define ZDC_CAP (64u << 10)    // window bytes
+#define ZDC_HIST (16u << 10)   // history kept when the window slides
+struct ZdWindow {
+	uintptr_t bias;  // shared-memory address frame position q maps to is bias + q, for q in [lo, written)
+	u64 lo;          // positions below are in global memory only (and everything below `lo` IS there)
+	const u8* g;     // the frame's output in global memory
+	ZG_DEV u8* dst(u64 pos) const { return (u8*)(bias + (uintptr_t)pos); }
+	ZG_DEV void lane_copy(u64 dpos, u64 spos, u32 n) const {
+		for (u32 k0 = 0; k0 < n; k0 += 16) {
+			u64 q = spos + k0;
+			u32 m = zg_min<u32>(16u, n - k0);
+			u8* dp = dst(dpos + k0);
+			if (q >= lo) zd_lane_copy<false>(dp, (const u8*)dst(q), m);
+			else if (q + m <= lo) zd_lane_copy<true>(dp, g + q, m);
+			else
+				for (u32 i = 0; i < m; i++) dp[i] = q + i >= lo ? *dst(q + i) : (u8)zd_ldb<true>(g + q + i);
+		}
+	}
+	ZG_DEV void lane_overlap(u64 dpos, u32 off, u32 ml) const {
+		u32 done = 0;
+		while (done < ml) {
+			u32 c = zg_min<u32>(done + off, ml - done);
+			lane_copy(dpos + done, dpos - off, c);
+			done += c;
+		}
+	}
+	ZG_DEV void warp_copy(u64 dpos, u64 spos, u32 n) const {
+		u32 far = spos < lo ? (u32)zg_min<u64>(n, lo - spos) : 0u;
+		if (far) zg_warp_copy_t<true>(dst(dpos), g + spos, far);
+		if (n > far) zg_warp_copy_t<false>(dst(dpos + far), (const u8*)dst(spos + far), n - far);
+	}
+	ZG_DEV void warp_match(u64 dpos, u32 off, u32 ml) const {  // off < ml: the first period, then the match feeds on itself
+		warp_copy(dpos, dpos - off, off);
+		__syncwarp();
+		zd_warp_match<false>(dst(dpos + off), off, ml - off);
+	}
+};
+
+struct ZdcState {
+	u8* buf;        // the window's shared memory (ZDC_CAP + 32 bytes, 16-byte aligned)
+	u8* gout;       // the frame's output in global memory
+	u64 abase;      // frame position of buf[0] (a multiple of 16)
+	u64 lo;         // see ZdWindow
+	u64 flushed;    // positions below are in global memory
+};
+ZG_DEV ZdWindow zdc_window(const ZdcState& S) { return ZdWindow{(uintptr_t)S.buf - (uintptr_t)S.abase, S.lo, S.gout}; }
+// everything produced so far into global memory
+ZG_DEV void zdc_flush(ZdcState& S, u64 pos) {
+	if (pos > S.flushed) zg_warp_copy(S.gout + S.flushed, S.buf + (S.flushed - S.abase), (u32)(pos - S.flushed));
+	S.flushed = pos;
+	__syncwarp();
+}
+// make room for `need` more bytes at `pos`: false when they cannot fit the window at all (the caller then works in global memory)
+ZG_DEV bool zdc_room(ZdcState& S, u64 pos, u32 need) {
+	if (pos + need <= S.abase + ZDC_CAP) return true;
+	if (need > ZDC_CAP - ZDC_HIST - 16u) return false;
+	zdc_flush(S, pos);
+	// slide: keep the last ZDC_HIST bytes (what the matches right ahead are most likely to read)
+	u64 nlo = zg_max<u64>(S.lo, pos > ZDC_HIST ? pos - ZDC_HIST : 0);
+	u64 nab = nlo & ~(u64)15;
+	u32 keep = (u32)(pos - nab), shift = (u32)(nab - S.abase);
+	u32 lane = zg_lane();
+	if (shift) {
+		for (u32 v0 = 0; v0 < keep; v0 += 512) {  // forward, 16 bytes per lane: reads of a round finish before its writes
+			u32 v = v0 + 16 * lane;
+			uint4 x = make_uint4(0, 0, 0, 0);
+			if (v < keep) x = *(const uint4*)(S.buf + shift + v);
+			__syncwarp();
+			if (v < keep) *(uint4*)(S.buf + v) = x;
+			__syncwarp();
+		}
+	}
+	S.abase = nab;
+	S.lo = nlo;
+	return true;
+}
+// leave the window: what follows is written to global memory directly
+ZG_DEV void zdc_reset(ZdcState& S, u64 pos_before, u64 pos_after) {
+	zdc_flush(S, pos_before);
+	S.abase = pos_after & ~(u64)15;
+	S.lo = S.flushed = pos_after;
+}
+
+__global__ void __launch_bounds__(32)
+k_zds_chain(ZdsJob J, const u32* __restrict__ chain_list, u32 nchain, const u64* __restrict__ first, const u32* __restrict__ nblk, u32 J0, u32 w,
+            u32* queue) {
+	ZG_DYN_SMEM(u8, smem);
+	u32 lane = threadIdx.x & 31;
+	for (;;) {
+		u32 ci = 0;
+		if (lane == 0) ci = atomicAdd(queue, 1u);
+		ci = __shfl_sync(ZG_FULL, ci, 0);
+		if (ci >= nchain) break;
+		u32 k = chain_list[ci];
+		u64 f0 = first[k];
+		u32 hi = zg_min<u32>(nblk[k], J0 + w);
+		const u8* fsrc = J.archive + J.off[k];
+		u64 cap = J.ulen[k];
+		ZdcState S;
+		S.buf = smem;
+		S.gout = J.out + J.out_off[k];
+		u64 pos = J.out_pos[f0 + J0];
+		S.abase = pos & ~(u64)15;
+		S.lo = S.flushed = pos;
+		u32 err = zds_ld_flag_warp(&J.f_status[k]);
+		for (u32 j = J0; j < hi && err == ZS_OK; j++) {
+			u64 g = f0 + j;
+			ZdsBlk B = J.blk[g];
+			u32 type = (B.hdr >> 1) & 3, bsize = B.hdr >> 3;
+			const u8* body = fsrc + B.ip + 3;
+			u64 o = J.out_pos[g];
+			if (type != 2) {
+				// Raw / RLE block: straight to global memory, the window starts over behind it
+				zdc_reset(S, o, o + bsize);
+				if (type == 0) zg_warp_copy(S.gout + o, body, bsize);
+				else zg_warp_fill(S.gout + o, body[0], bsize);
+				__syncwarp();
+				continue;
+			}
+			ZdLitHdr h;
+			zd_lit_header(body, bsize, h);  // validated by k_zds_modes
+			// this block's position among the chunk's items: its staging offsets are indexed by item
+			u32 it = J.item_of[g];
+			const u8* lit = h.ltype == 0 ? body + h.hdr : h.ltype == 1 ? body : J.lit_stage + J.lit_off[it];
+			bool lit_rle = h.ltype == 1;
+			u32 rle_byte = lit_rle ? body[h.hdr] : 0;
+			u32 r0 = J.rep_in[3 * g], r1 = J.rep_in[3 * g + 1], r2 = J.rep_in[3 * g + 2];
+			const u64* seqs = J.seq_stage + J.seq_off[it];
+			u32 nseq = B.nseq, lpos = 0;
+			u64 sq = lane < nseq ? seqs[lane] : 0;
+			for (u32 s0 = 0; s0 < nseq && err == ZS_OK; s0 += 32) {
+				u64 sq_next = s0 + 32 + lane < nseq ? seqs[s0 + 32 + lane] : 0;
+				bool act = s0 + lane < nseq;
+				u32 rof = zds_resolve((u32)sq & ZD_OFF_MAX, r0, r1, r2);
+				u32 ll = (u32)(sq >> 28) & 0x3ffffu, ml = (u32)(sq >> 46);
+				u32 row = zg_warp_sum(act ? ll + ml : 0u);
+				if (__any_sync(ZG_FULL, act && rof == 0)) err = ZS_E_CORRUPT;
+				else {
+					sq = (sq & ~(u64)ZD_OFF_MAX) | rof;
+					u32 cnt = zg_min<u32>(32u, nseq - s0);
+					if (zdc_room(S, o, row)) err = zd_exec_row(sq, cnt, zdc_window(S), o, 0, cap, lit, lit_rle, rle_byte, h.regen, lpos);
+					else {  // a row larger than the window: in global memory (matches of tens of KiB: the hop latency does not matter)
+						u64 o0 = o;
+						zdc_flush(S, o0);
+						err = zd_exec_row(sq, cnt, ZdDirect<true>{S.gout}, o, 0, cap, lit, lit_rle, rle_byte, h.regen, lpos);
+						__syncwarp();
+						S.abase = o & ~(u64)15;
+						S.lo = S.flushed = o;
+					}
+				}
+				sq = sq_next;
+			}
+			if (err == ZS_OK) {
+				u32 rest = h.regen - lpos;
+				if (o + rest > cap) err = ZS_E_DST_SMALL;
+				else if (rest) {
+					if (zdc_room(S, o, rest)) {
+						u8* d = zdc_window(S).dst(o);
+						if (lit_rle) zg_warp_fill(d, rle_byte, rest);
+						else zg_warp_copy(d, lit + lpos, rest);
+					} else {
+						zdc_reset(S, o, o + rest);
+						if (lit_rle) zg_warp_fill(S.gout + o, rle_byte, rest);
+						else zg_warp_copy(S.gout + o, lit + lpos, rest);
+					}
+					o += rest;
+				}
+			}
+			__syncwarp();
+			if (err == ZS_OK) pos = o;
+		}
+		if (err == ZS_OK) zdc_flush(S, pos);
+		else if (lane == 0) atomicCAS(&J.f_status[k], (u32)ZS_OK, err);
+		__syncwarp();
 	}
 }
 
@@ -789,10 +982,15 @@ k_zds_finish(const u8* __restrict__ archive, const u64* __restrict__ off, const 
 // frames of this many bytes and more are staged (two blocks at least)
 static u64 g_zds_split_min = (u64)ZS_BLOCK_MAX + 1;
 extern "C" void zg_internal_set_decode_split_min(u64 v) { g_zds_split_min = v ? v : (u64)ZS_BLOCK_MAX + 1; }
+// 0: dependent blocks wait on per-block flags (k_zds_exec); 1: frames with dependent blocks go to the chain executor when
+// they fit the machine; 2: always
+static u32 g_zds_chain_mode = 1;
+extern "C" void zg_internal_set_decode_chain_mode(u32 v) { g_zds_chain_mode = v; }
 static u32 g_zds_chunk_items = ZDS_CHUNK_ITEMS;
 extern "C" void zg_internal_set_decode_chunk_blocks(u32 v) { g_zds_chunk_items = v ? v : ZDS_CHUNK_ITEMS; }  // (tests shrink it)
 // what the last zg_zstd_decode_run did: {frames, work items (frames + blocks of staged frames), frames decoded twice
-// (always 0: there is no second pass any more), staged frames, staged blocks, blocks that waited for earlier output, chunks}
+// (always 0: there is no second pass any more), staged frames, staged blocks, blocks that read earlier blocks, chunks,
+// frame-chunks run by the chain executor}
 u64 g_zd_stats[8];
 extern "C" void zg_internal_decode_stats(u64 out[3]) {
 	for (int i = 0; i < 3; i++) out[i] = g_zd_stats[i];
@@ -849,7 +1047,8 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 	if (S.blk.reserve(nblocks * sizeof(ZdsBlk)) || S.res.reserve(nblocks * sizeof(ZdsRes)) || S.out_pos.reserve(nblocks * 8) ||
 	    S.rep_in.reserve(nblocks * 12) || S.dep.reserve(nblocks * 4) || S.done.reserve(nblocks * 4) || S.tail.reserve(n * 8) ||
 	    S.f_out.reserve(n * 8) || S.f_rep.reserve(n * 12) || S.f_status.reserve(n * 4) || S.done_upto.reserve(n * 4) ||
-	    S.jbase.reserve((max_nb + 1) * 4) || S.cursor.reserve((max_nb + 1) * 4) || S.hh.reserve((max_nb + 2) * 8) || S.queue.reserve(64))
+	    S.jbase.reserve((max_nb + 1) * 4) || S.cursor.reserve((max_nb + 1) * 4) || S.hh.reserve((max_nb + 2) * 8) || S.queue.reserve(64) ||
+	    S.f_chain.reserve(n * 4) || S.item_of.reserve(nblocks * 4) || S.chain_list.reserve(nmulti * 4))
 		return ZG_ERR(ZG_error_memory_allocation);
 	u32 gm = (u32)((nmulti + 127) / 128);
 	ZG_LAUNCH(k_zds_emit, gm, 128, 0, s, archive, archive_len, off, len, ulen, out_off, out_cap, S.multi.as<u32>(), nmulti, g_zds_split_min,
@@ -921,11 +1120,21 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 	J.done = S.done.as<u32>();
 	J.done_upto = S.done_upto.as<u32>();
 	J.f_status = S.f_status.as<u32>();
+	J.f_chain = S.f_chain.as<u32>();
+	J.item_of = S.item_of.as<u32>();
+	size_t smem_c = ZDC_CAP + 48;
+	static ZgPerDevice attr_dev_c;
+	bool& attr_set_c = *attr_dev_c.slot();
+	if (!attr_set_c) {
+		if (cudaFuncSetAttribute(k_zds_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c) != cudaSuccess) return ZG_ERR(ZG_error_device);
+		attr_set_c = true;
+	}
 	u64* totals = (u64*)S.tot.p + 4;  // [4] sequences, [5] literal bytes, [6] blocks that wait
 	cudaMemsetAsync(totals + 2, 0, 8, s);
 	for (auto& c : chunks) {
 		ZG_LAUNCH(k_zds_chunk_items, (u32)((nmulti + 3) / 4), 128, 0, s, S.multi.as<u32>(), nmulti, S.first.as<u64>(), S.nblk.as<u32>(),
-		          S.blk.as<ZdsBlk>(), c.J, c.w, S.jbase.as<u32>(), S.cursor.as<u32>(), S.items.as<u32>(), S.seq_cnt.as<u64>(), S.lit_cnt.as<u64>());
+		          S.blk.as<ZdsBlk>(), c.J, c.w, S.jbase.as<u32>(), S.cursor.as<u32>(), S.items.as<u32>(), S.item_of.as<u32>(), S.seq_cnt.as<u64>(),
+		          S.lit_cnt.as<u64>());
 		ZG_COUNT_LAUNCH();
 		size_t r = zg_scan_run(s, w.tiles, S.seq_cnt.as<u64>(), c.items, 0, S.seq_off.as<u64>(), totals);
 		if (!zg_is_error(r)) r = zg_scan_run(s, w.tiles, S.lit_cnt.as<u64>(), c.items, 0, S.lit_off.as<u64>(), totals + 1);
@@ -943,10 +1152,27 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 		cudaMemsetAsync(S.queue.p, 0, 16, s);
 		zg_prof_begin(ZG_K_DECODE, s);
 		ZG_LAUNCH(k_zds_entropy, grid_e, ZDS_WARPS * 32, smem, s, J, S.tabs.as<u32>(), S.queue.as<u32>(), want);
+		cudaMemsetAsync(totals + 3, 0, 8, s);
 		ZG_LAUNCH(k_zds_frame_scan, gm, 128, 0, s, J, S.multi.as<u32>(), nmulti, S.first.as<u64>(), S.nblk.as<u32>(), c.J, c.w, S.f_out.as<u64>(),
-		          S.f_rep.as<u32>());
+		          S.f_rep.as<u32>(), S.chain_list.as<u32>(), (unsigned long long*)(totals + 3));
+		// frames with blocks that read earlier blocks: by the chain executor (one warp and a shared-memory window per
+		// frame) when they all fit the machine at once, else block by block behind per-block flags
+		u64 nchain = 0;
+		if (g_zds_chain_mode) {
+			if (zg_publish(s, totals + 3, h + 7, 8) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) return ZG_ERR(ZG_error_device);
+			nchain = h[7];
+		}
+		const u32 chain_slots = sms * (u32)(227u * 1024u / (ZDC_CAP + 1024u));
+		bool use_chain = g_zds_chain_mode == 2 ? nchain > 0 : (nchain > 0 && nchain <= (u64)chain_slots * 4);
+		g_zd_stats[7] += use_chain ? nchain : 0;
 		u32 grid_x = (u32)zg_min<u64>(((u64)c.items + ZDS_WARPS - 1) / ZDS_WARPS, (u64)sms * ZDS_EXEC_CTAS);
-		ZG_LAUNCH(k_zds_exec, grid_x, ZDS_WARPS * 32, 0, s, J, S.first.as<u64>(), S.queue.as<u32>() + 1);
+		ZG_LAUNCH(k_zds_exec, grid_x, ZDS_WARPS * 32, 0, s, J, S.first.as<u64>(), S.queue.as<u32>() + 1, use_chain ? 1u : 0u);
+		if (use_chain) {
+			u32 grid_c = (u32)zg_min<u64>(nchain, (u64)chain_slots);
+			ZG_LAUNCH(k_zds_chain, grid_c, 32, smem_c, s, J, S.chain_list.as<u32>(), (u32)nchain, S.first.as<u64>(), S.nblk.as<u32>(), c.J, c.w,
+			          S.queue.as<u32>() + 2);
+			ZG_COUNT_LAUNCH();
+		}
 		zg_prof_end(ZG_K_DECODE, s);
 		ZG_LAUNCH(k_zds_count_deps, (c.items + 255) / 256, 256, 0, s, S.blk.as<ZdsBlk>(), S.dep.as<u32>(), S.items.as<u32>(), c.items,
 		          (unsigned long long*)(totals + 2));
