@@ -642,6 +642,8 @@ def main():
     if os.environ.get("ZG_DECODE_BATCHING"):  # tuning aid: "cap_div,min_batch_bytes,floor_bytes"
         a, b, c3 = os.environ["ZG_DECODE_BATCHING"].split(",")
         lib.dll.zg_internal_set_decode_batching(C.c_uint32(int(a)), C.c_uint32(int(b)), C.c_uint32(int(c3)))
+    if os.environ.get("ZG_CHAIN_MODE"):  # tuning aid: 0 per-block flags, 1 chain executor when the frames fit, 2 always
+        lib.dll.zg_internal_set_decode_chain_mode(C.c_uint32(int(os.environ["ZG_CHAIN_MODE"])))
     if os.environ.get("ZG_SLICE_MB"):  # tuning aid: host-API slice size
         lib.dll.zg_internal_set_slice_bytes(C.c_uint64(int(os.environ["ZG_SLICE_MB"]) << 20))
     if os.environ.get("ZG_PACK_SLICE_MB"):  # tuning aid: host-API slice size, pack only

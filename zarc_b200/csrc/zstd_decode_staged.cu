@@ -862,7 +862,11 @@ ZG_DEV void zdc_reset(ZdcState& S, u64 pos_before, u64 pos_after) {
 	S.lo = S.flushed = pos_after;
 }
 
-__global__ void __launch_bounds__(32)
+#ifdef ZG_EMU
+__global__ void
+#else
+__global__ void __maxnreg__(128)
+#endif
 k_zds_chain(ZdsJob J, const u32* __restrict__ chain_list, u32 nchain, const u64* __restrict__ first, const u32* __restrict__ nblk, u32 J0, u32 w,
             u32* queue) {
 	ZG_DYN_SMEM(u8, smem);
