@@ -149,3 +149,46 @@ def test_one_shot_and_streaming_api(emu):
         pos += inb.pos
     assert got == data and pos == len(frame)
     emu.zg_dctx_free(d)
+
+
+def test_streaming_with_tiny_and_odd_gulps_and_the_streaming_hasher(emu):
+    """The frame header and the 3-byte block headers may straddle any two calls; the streaming Hasher sees the same
+    chunks the FrameIterator would feed it (decode/frame_iterator.rs:94-103)."""
+    import ctypes as C
+    from zarc_b200._lib import InBuffer, OutBuffer
+
+    rng = np.random.default_rng(3)
+    for data, level in ((text(300_000, 9) + rand(140_000, 4) + bytes(200_000), 3), (b"", 3), (b"x", 1), (text(70_000, 2), 9)):
+        frame = ref_path.ref_compress(data, level=level)
+        archive = frame + b"\x28\xb5\x2f\xfdjunk of a next frame"
+        for gulps in ("bytes", "random"):
+            d = emu.zg_dctx_create()
+            h = emu.zg_hasher_new()
+            pos, got, done = 0, b"", False
+            while not done:
+                n = 1 if (gulps == "bytes" and pos < 40) else int(rng.integers(1, 70_000))
+                gulp = archive[pos : pos + n]
+                ib = C.create_string_buffer(gulp, len(gulp))
+                inb = InBuffer(C.cast(ib, C.c_void_p), len(gulp), 0)
+                while True:
+                    cap = int(rng.integers(1, 200_000))
+                    ob = C.create_string_buffer(cap)
+                    outb = OutBuffer(C.cast(ob, C.c_void_p), cap, 0)
+                    hint = emu.check(emu.zg_decompress_stream(d, C.byref(outb), C.byref(inb)))
+                    chunk = ob.raw[: outb.pos]
+                    got += chunk
+                    emu.check(emu.zg_hasher_update(h, chunk, len(chunk)))
+                    if hint == 0:
+                        done = True
+                        break
+                    if outb.pos < cap and inb.pos == inb.size:
+                        break
+                pos += inb.pos
+            assert got == data and pos == len(frame)
+            dig = C.create_string_buffer(32)
+            emu.check(emu.zg_hasher_finalize(h, dig))
+            assert dig.raw == _b3(data)
+            emu.check(emu.zg_hasher_finalize(h, dig))  # does not consume
+            assert dig.raw == _b3(data)
+            emu.zg_hasher_free(h)
+            emu.zg_dctx_free(d)

@@ -125,10 +125,27 @@ struct zg_dctx {
 	cudaStream_t s_in = nullptr, s_out = nullptr;
 	ZgBuf d_archive, d_out, d_meta;  // one-shot / streaming paths
 	ZgHostBuf h_first, h_small;
-	// streaming state (zg_decompress_stream)
-	std::vector<uint8_t> in_acc, out_acc;
-	size_t out_pos = 0;
-	int stage = 0;  // 0 collecting input, 1 flushing output
+	// streaming state (zg_decompress_stream): the frame is collected and decoded ON THE DEVICE; the host keeps only
+	// the header walk's few bytes of state, so a multi-GiB frame costs no host memory (the reference streams too)
+	struct Stream {
+		ZgBuf in, out;             // device: the frame so far / the decoded frame
+		uint64_t in_len = 0;       // frame bytes received
+		uint8_t carry[24];         // the last bytes received (a 3-byte block header or the frame header may straddle two calls)
+		uint32_t ncarry = 0;
+		bool have_header = false;
+		uint32_t checksum = 0, fcs_len = 0;
+		uint64_t fcs = 0, blocks = 0;
+		uint64_t next_hdr = 0;     // frame offset of the next block header to read
+		uint64_t frame_end = 0;    // frame length, known once the last block's header has been seen (else 0)
+		uint64_t out_len = 0, out_pos = 0;
+		int stage = 0;             // 0 collecting input, 1 handing out output
+		void reset() {
+			in_len = ncarry = checksum = fcs_len = 0;
+			have_header = false;
+			fcs = blocks = next_hdr = frame_end = out_len = out_pos = 0;
+			stage = 0;
+		}
+	} sm;
 };
 
 // device-pointer core of unpack: decode, verify sizes/checksums, optional BLAKE3 verify, first error
@@ -322,23 +339,50 @@ size_t zg_xxh64_batch(const uint8_t* blob, const uint64_t* off, const uint64_t* 
 // update() buffers; finalize() hashes the buffered bytes on the GPU (the digest of a stream is
 // only observable at finalize, so this is semantically identical).
 struct zg_hasher {
-	std::vector<uint8_t> acc;
+	ZgBuf dev, meta, out;   // the content so far lives ON THE DEVICE (the host keeps nothing)
+	ZgB3Work b3;
+	uint64_t len = 0;
 };
-zg_hasher* zg_hasher_new(void) { return new (std::nothrow) zg_hasher(); }
-static size_t hasher_update_impl(zg_hasher* h, const void* data, size_t len) {
-	const uint8_t* p = (const uint8_t*)data;
-	h->acc.insert(h->acc.end(), p, p + len);
-	return 0;
+zg_hasher* zg_hasher_new(void) {
+	if (dev_count() <= 0) return nullptr;
+	return new (std::nothrow) zg_hasher();
 }
 size_t zg_hasher_update(zg_hasher* h, const void* data, size_t len) {
+	ZG_NEED_DEVICE();
 	if (!h || (!data && len)) return ZG_ERR(ZG_error_GENERIC);
-	ZG_GUARD(hasher_update_impl(h, data, len));
+	if (!len) return 0;
+	if (h->len + len > h->dev.cap) {
+		ZgBuf nb;
+		size_t want = (h->len + len) + (h->len + len) / 2 + 4096;
+		ZG_ALLOC(nb.reserve(want));
+		if (h->len) ZG_CUDA(cudaMemcpy(nb.p, h->dev.p, h->len, cudaMemcpyDeviceToDevice));
+		h->dev.release();
+		h->dev = nb;
+	}
+	ZG_CUDA(cudaMemcpy(h->dev.as<u8>() + h->len, data, len, cudaMemcpyHostToDevice));
+	h->len += len;
+	return 0;
 }
 size_t zg_hasher_finalize(zg_hasher* h, uint8_t out[32]) {
+	ZG_NEED_DEVICE();
 	if (!h) return ZG_ERR(ZG_error_GENERIC);
-	return zg_blake3(h->acc.data(), h->acc.size(), out);
+	ZG_ALLOC(h->dev.reserve(16));
+	ZG_ALLOC(h->meta.reserve(16));
+	ZG_ALLOC(h->out.reserve(32));
+	uint64_t m[2] = {0, h->len};
+	ZG_CUDA(cudaMemcpy(h->meta.p, m, 16, cudaMemcpyHostToDevice));
+	ZG_TRY(zg_blake3_run(0, h->b3, h->dev.as<u8>(), h->meta.as<u64>(), h->meta.as<u64>() + 1, 1, h->out.as<u8>()));
+	ZG_CUDA(cudaMemcpy(out, h->out.p, 32, cudaMemcpyDeviceToHost));
+	return 0;
 }
-void zg_hasher_free(zg_hasher* h) { delete h; }
+void zg_hasher_free(zg_hasher* h) {
+	if (!h) return;
+	h->dev.release();
+	h->meta.release();
+	h->out.release();
+	zg_b3work_free(h->b3);
+	delete h;
+}
 
 // ---------------------------------------------------------------------------------------------
 // decompression context
@@ -358,7 +402,7 @@ void zg_dctx_free(zg_dctx* d) {
 	cudaStreamSynchronize(d->stream);
 	d->zd.release();
 	zg_b3work_free(d->b3);
-	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->vspan, &d->d_archive,
+	for (ZgBuf* b : {&d->status, &d->produced, &d->cksums, &d->got_digests, &d->first, &d->tiles, &d->packed_off, &d->vspan, &d->sm.in, &d->sm.out, &d->d_archive,
 	                 &d->d_meta, &d->d_out})
 		b->release();
 	for (auto& st : d->hstage) {
@@ -561,19 +605,9 @@ size_t zg_unpack_batch(zg_dctx* d, const uint8_t* archive, uint64_t archive_len,
 	ZG_GUARD(unpack_batch_impl(d, archive, archive_len, n, off, len, ulen, digests, out, out_cap, out_off, ok, status));
 }
 
-size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t n) {
-	ZG_NEED_DEVICE();
-	if (!d) return ZG_ERR(ZG_error_GENERIC);
-	uint64_t bound = 0;
-	bool has_fcs = false;
-	size_t fsz = host_frame_size((const uint8_t*)src, n, &bound, &has_fcs);
-	if (fsz == 0) return ZG_ERR(ZG_error_srcSize_wrong);
-	if (zg_is_error(fsz)) return fsz;
-	if (has_fcs && bound > cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
+// one frame already on the device (d_frame, fsz bytes) -> d_out (ocap bytes); returns the bytes produced
+static size_t decompress_dev(zg_dctx* d, const u8* d_frame, u64 fsz, u8* d_out, u64 ocap) {
 	cudaStream_t s = d->stream;
-	u64 ocap = bound;
-	ZG_ALLOC(d->d_archive.reserve(fsz + 16));
-	ZG_ALLOC(d->d_out.reserve(ocap + 16));
 	ZG_ALLOC(d->d_meta.reserve(64));
 	ZG_ALLOC(d->produced.reserve(8));
 	ZG_ALLOC(d->cksums.reserve(8));
@@ -585,22 +619,38 @@ size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t 
 	hm[2] = ocap;
 	hm[3] = 0;
 	u64* m = d->d_meta.as<u64>();
-	ZG_CUDA(cudaMemcpyAsync(d->d_archive.p, src, fsz, cudaMemcpyHostToDevice, s));
 	ZG_CUDA(cudaMemcpyAsync(m, hm, 32, cudaMemcpyHostToDevice, s));
-	ZG_TRY(zg_zstd_decode_run(s, d->zd, d->d_archive.as<u8>(), fsz, m, m + 1, m + 2, m + 3, 1, d->d_out.as<u8>(), ocap,
-	                          d->status.as<u32>(), d->produced.as<u64>(), d->cksums.as<u32>()));
+	ZG_TRY(zg_zstd_decode_run(s, d->zd, d_frame, fsz, m, m + 1, m + 2, m + 3, 1, d_out, ocap, d->status.as<u32>(), d->produced.as<u64>(),
+	                          d->cksums.as<u32>()));
 	// size is whatever the frame produced (FCS is checked inside the kernel when present)
 	ZG_CUDA(cudaMemcpyAsync(hm + 4, d->produced.p, 8, cudaMemcpyDeviceToHost, s));
 	ZG_CUDA(cudaStreamSynchronize(s));
 	u64 produced = hm[4];
 	hm[2] = produced;
 	ZG_CUDA(cudaMemcpyAsync(m + 2, hm + 2, 8, cudaMemcpyHostToDevice, s));
-	ZG_TRY(zg_unpack_finalize_run(s, d->d_out.as<u8>(), m + 3, m + 2, d->produced.as<u64>(), d->cksums.as<u32>(), d->status.as<u32>(), 1,
-	                              d->verify_checksum));
+	ZG_TRY(zg_unpack_finalize_run(s, d_out, m + 3, m + 2, d->produced.as<u64>(), d->cksums.as<u32>(), d->status.as<u32>(), 1, d->verify_checksum));
 	u32* hst = (u32*)(hm + 5);
 	ZG_CUDA(cudaMemcpyAsync(hst, d->status.p, 4, cudaMemcpyDeviceToHost, s));
 	ZG_CUDA(cudaStreamSynchronize(s));
 	if (*hst) return ZG_ERR((size_t)*hst);
+	return produced;
+}
+
+size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t n) {
+	ZG_NEED_DEVICE();
+	if (!d) return ZG_ERR(ZG_error_GENERIC);
+	uint64_t bound = 0;
+	bool has_fcs = false;
+	size_t fsz = host_frame_size((const uint8_t*)src, n, &bound, &has_fcs);
+	if (fsz == 0) return ZG_ERR(ZG_error_srcSize_wrong);
+	if (zg_is_error(fsz)) return fsz;
+	if (has_fcs && bound > cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
+	u64 ocap = bound;
+	ZG_ALLOC(d->d_archive.reserve(fsz + 16));
+	ZG_ALLOC(d->d_out.reserve(ocap + 16));
+	ZG_CUDA(cudaMemcpyAsync(d->d_archive.p, src, fsz, cudaMemcpyHostToDevice, d->stream));
+	size_t produced = decompress_dev(d, d->d_archive.as<u8>(), fsz, d->d_out.as<u8>(), ocap);
+	if (zg_is_error(produced)) return produced;
 	if (produced > cap) return ZG_ERR(ZG_error_dstSize_tooSmall);
 	if (produced) ZG_CUDA(cudaMemcpy(dst, d->d_out.p, produced, cudaMemcpyDeviceToHost));
 	return produced;
@@ -609,62 +659,142 @@ size_t zg_decompress(zg_dctx* d, void* dst, size_t cap, const void* src, size_t 
 // DCtx::decompress_stream contract (decode/zstd_iterator.rs:104-107,126-129): consume input until the
 // frame is complete, decode it on the GPU, then hand the output out as space allows.  Returns 0
 // when the frame is fully decoded and flushed, otherwise a non-zero hint.
+// grow a device buffer keeping its first `keep` bytes
+static cudaError_t dev_grow_keep(ZgBuf& b, size_t need, size_t keep, cudaStream_t s) {
+	if (need <= b.cap) return cudaSuccess;
+	ZgBuf nb;
+	cudaError_t e = nb.reserve(need + need / 2);
+	if (e != cudaSuccess) return e;
+	if (keep && b.p) {
+		e = cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, s);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess) {
+			nb.release();
+			return e;
+		}
+	}
+	b.release();
+	b = nb;
+	return cudaSuccess;
+}
+// byte at frame offset `pos` out of (carry, the bytes offered now); the caller only asks for offsets that are in reach
+static inline uint8_t stream_byte(const zg_dctx::Stream& S, const uint8_t* src, uint64_t pos) {
+	return pos >= S.in_len ? src[pos - S.in_len] : S.carry[S.ncarry - (S.in_len - pos)];
+}
 static size_t decompress_stream_impl(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* input) {
 	ZG_NEED_DEVICE();
 	if (!d || !output || !input) return ZG_ERR(ZG_error_GENERIC);
 	if (input->pos > input->size || output->pos > output->size) return ZG_ERR(ZG_error_srcSize_wrong);
-	if (d->stage == 0) {
+	zg_dctx::Stream& S = d->sm;
+	cudaStream_t s = d->stream;
+	if (S.stage == 0) {
 		const uint8_t* src = (const uint8_t*)input->src + input->pos;
 		size_t avail = input->size - input->pos;
-		size_t before = d->in_acc.size();
-		d->in_acc.insert(d->in_acc.end(), src, src + avail);
-		uint64_t bound = 0;
-		size_t fsz = host_frame_size(d->in_acc.data(), d->in_acc.size(), &bound);
-		if (zg_is_error(fsz)) {
-			d->in_acc.clear();
-			return fsz;
+		uint64_t have = S.in_len + avail;  // frame bytes in reach: [0, have)
+		// ---- header walk (frame header, then 3-byte block headers): no content byte is looked at on the host ----
+		if (!S.have_header && have >= 5) {
+			uint8_t hb[18];
+			uint32_t nh = (uint32_t)(have < 18 ? have : 18);
+			for (uint32_t i = 0; i < nh; i++) hb[i] = stream_byte(S, src, i);
+			uint32_t magic = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) | ((uint32_t)hb[3] << 24);
+			if (magic != 0xFD2FB528u) {
+				S.reset();
+				return ZG_ERR(ZG_error_prefix_unknown);
+			}
+			uint32_t desc = hb[4];
+			if (desc & 8) {
+				S.reset();
+				return ZG_ERR(ZG_error_frameParameter_unsupported);
+			}
+			uint32_t fcs_flag = desc >> 6, single = (desc >> 5) & 1, did_flag = desc & 3;
+			uint32_t ip = 5 + (single ? 0 : 1) + (did_flag == 3 ? 4 : did_flag);
+			uint32_t fcs_len = fcs_flag == 0 ? single : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+			if (have >= ip + fcs_len) {
+				uint64_t fcs = 0;
+				for (uint32_t i = 0; i < fcs_len; i++) fcs |= (uint64_t)hb[ip + i] << (8 * i);
+				if (fcs_len == 2) fcs += 256;
+				S.have_header = true;
+				S.checksum = (desc >> 2) & 1;
+				S.fcs_len = fcs_len;
+				S.fcs = fcs;
+				S.next_hdr = ip + fcs_len;
+			}
 		}
-		if (fsz == 0) {  // frame incomplete: everything offered belongs to it
-			input->pos = input->size;
-			return 3;  // at least one more block header
+		while (S.have_header && !S.frame_end && S.next_hdr + 3 <= have) {
+			uint32_t bh = (uint32_t)stream_byte(S, src, S.next_hdr) | ((uint32_t)stream_byte(S, src, S.next_hdr + 1) << 8) |
+			              ((uint32_t)stream_byte(S, src, S.next_hdr + 2) << 16);
+			uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+			if (type == 3) {
+				S.reset();
+				return ZG_ERR(ZG_error_corruption_detected);
+			}
+			S.next_hdr += 3 + (type == 1 ? 1 : bsize);
+			S.blocks++;
+			if (last) S.frame_end = S.next_hdr + (S.checksum ? 4 : 0);
 		}
-		input->pos += fsz - before;  // never consume past the end of this frame
-		d->in_acc.resize(fsz);
-		d->out_acc.assign(bound ? bound : 1, 0);
-		size_t r = zg_decompress(d, d->out_acc.data(), bound, d->in_acc.data(), fsz);
-		d->in_acc.clear();
+		// ---- the bytes of this frame go to the device; never consume past the end of the frame ----
+		size_t take = avail;
+		if (S.frame_end && S.in_len + take > S.frame_end) take = (size_t)(S.frame_end - S.in_len);
+		if (take) {
+			if (dev_grow_keep(S.in, S.in_len + take + 16, S.in_len, s) != cudaSuccess) {
+				S.reset();
+				return ZG_ERR(ZG_error_memory_allocation);
+			}
+			ZG_CUDA(cudaMemcpyAsync(S.in.as<u8>() + S.in_len, src, take, cudaMemcpyHostToDevice, s));
+			ZG_CUDA(cudaStreamSynchronize(s));  // the caller may reuse its input buffer as soon as we return
+			// keep the last bytes for headers that straddle this call and the next
+			uint8_t nc[24];
+			uint32_t keep = (uint32_t)((S.ncarry + take) < 24 ? (S.ncarry + take) : 24);
+			for (uint32_t i = 0; i < keep; i++) {
+				uint64_t pos = S.in_len + take - keep + i;
+				nc[i] = stream_byte(S, src, pos);
+			}
+			memcpy(S.carry, nc, keep);
+			S.ncarry = keep;
+			S.in_len += take;
+			input->pos += take;
+		}
+		if (!S.frame_end || S.in_len < S.frame_end) {
+			// frame incomplete: hint = what is known to be missing, at least one more block header
+			if (S.frame_end) return (size_t)(S.frame_end - S.in_len);
+			return S.have_header && S.next_hdr + 3 > S.in_len ? (size_t)(S.next_hdr + 3 - S.in_len) : 3;
+		}
+		// ---- frame complete: decode it on the device ----
+		uint64_t bound = S.fcs_len ? S.fcs : S.blocks * 131072ull;
+		if (S.fcs_len && S.fcs > S.blocks * 131072ull) {  // (a frame cannot regenerate more than 128 KiB per block)
+			S.reset();
+			return ZG_ERR(ZG_error_corruption_detected);
+		}
+		if (S.out.reserve(bound + 16) != cudaSuccess) {
+			S.reset();
+			return ZG_ERR(ZG_error_memory_allocation);
+		}
+		size_t r = decompress_dev(d, S.in.as<u8>(), S.frame_end, S.out.as<u8>(), bound);
 		if (zg_is_error(r)) {
-			d->out_acc.clear();
+			S.reset();
 			return r;
 		}
-		d->out_acc.resize(r);
-		d->out_pos = 0;
-		d->stage = 1;
+		S.out_len = r;
+		S.out_pos = 0;
+		S.stage = 1;
 	}
 	size_t room = output->size - output->pos;
-	size_t left = d->out_acc.size() - d->out_pos;
+	size_t left = (size_t)(S.out_len - S.out_pos);
 	size_t take = room < left ? room : left;
-	if (take) memcpy((uint8_t*)output->dst + output->pos, d->out_acc.data() + d->out_pos, take);
+	if (take) ZG_CUDA(cudaMemcpy((uint8_t*)output->dst + output->pos, S.out.as<u8>() + S.out_pos, take, cudaMemcpyDeviceToHost));
 	output->pos += take;
-	d->out_pos += take;
-	if (d->out_pos == d->out_acc.size()) {
-		d->out_acc.clear();
-		d->out_pos = 0;
-		d->stage = 0;
+	S.out_pos += take;
+	if (S.out_pos == S.out_len) {
+		S.reset();
 		return 0;
 	}
-	return d->out_acc.size() - d->out_pos;
+	return (size_t)(S.out_len - S.out_pos);
 }
 size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* input) {
 	try {
 		return decompress_stream_impl(d, output, input);
-	} catch (...) {  // host staging could not be allocated: drop the half-collected frame, report it libzstd's way
-		if (d) {
-			d->in_acc.clear();
-			d->out_acc.clear();
-			d->out_pos = 0;
-			d->stage = 0;
-		}
+	} catch (...) {  // drop the half-collected frame, report it libzstd's way
+		if (d) d->sm.reset();
 		return ZG_ERR(ZG_error_memory_allocation);
 	}
 }
