@@ -415,6 +415,7 @@ def time_roundtrip(cx: Ctx, rt: RoundTrip, steps: int, warmup: int):
     total = cx.rank_max(e0.elapsed_time(e1)) / steps
     tp = cx.rank_max(sum(x.elapsed_time(y) for x, y in pk) / steps)
     tu = cx.rank_max(sum(x.elapsed_time(y) for x, y in up) / steps)
+    rt.step_ms = {"pack": [round(x.elapsed_time(y), 2) for x, y in pk], "unpack": [round(x.elapsed_time(y), 2) for x, y in up]}
     return total, tp, tu
 
 
@@ -429,7 +430,7 @@ def leg_roundtrip(cx: Ctx, glob, level: int, steps: int, warmup: int, checksum: 
         Ctot = cx.rank_sum(float(rt.nbytes[0]))
         return {"files": int(cx.rank_sum(float(rt.n))), "bytes": Btot, "unique_bytes": uniq, "compressed_bytes": Ctot, "ratio": uniq / max(Ctot, 1.0),
                 "pack_ms": tp, "unpack_ms": tu, "pack_gbs": Btot / tp / 1e6, "unpack_gbs": Utot / tu / 1e6,
-                "roundtrip_gbs": Btot / ms / 1e6, "steps": steps, "warmup": warmup, "checksum": checksum,
+                "roundtrip_gbs": Btot / ms / 1e6, "steps": steps, "warmup": warmup, "checksum": checksum, "rank0_step_ms": rt.step_ms,
                 "partition": "contiguous" if rt.plan.contiguous else "greedy", "roundtrip_verified": True}
     finally:
         rt.free()
@@ -544,7 +545,7 @@ def main():
     workload = workload_text(args.config, args, world, args.scaling)
     extras_on = []
     if args.extras == "auto":
-        extras_on = (["strong"] if world > 1 else []) + ["levels", "c4", "c3", "c5"] if args.config == "c2" else []
+        extras_on = (["strong"] if world > 1 else []) + ["levels", "c4", "c3", "nocksum", "c5"] if args.config == "c2" else []
     elif args.extras != "none":
         extras_on = [x for x in args.extras.split(",") if x]
 
@@ -877,7 +878,7 @@ def main():
             sample = corpus.c2_source_tree(total_bytes=int(args.levels_sample_gb * 1e9), seed=2)
             out = {}
             for lv in (1, 3, 9):
-                r = leg_roundtrip(cx, sample, lv, 2, 1)
+                r = leg_roundtrip(cx, sample, lv, 2, 2)
                 ref = ref_ratios.get(lv) if isinstance(ref_ratios, dict) else None
                 out[f"L{lv}"] = {"ratio": r["ratio"], "ratio_reference": ref, "ours_over_reference_size": (ref / r["ratio"]) if ref else None,
                                  "pack_gbs": r["pack_gbs"], "unpack_gbs": r["unpack_gbs"]}
