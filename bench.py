@@ -324,6 +324,7 @@ class RoundTrip:
         self.nbytes = np.zeros(1, dtype=np.uint64)
         self.total = None      # archive end offset (device scalar) after the last pack
         self.sel = None        # unpack list (multi-GPU with duplicates held by other ranks)
+        self.host_ms = []      # N > 1: per pack, host wall clock of [digests, dedup exchange, encode, offsets exchange]
 
     def pack(self):
         cx, lib = self.cx, self.cx.lib
@@ -334,16 +335,22 @@ class RoundTrip:
                                             self.cap, self.nbytes.ctypes.data))
             return
         # (1) digests (content_frame.rs:26) -> (2) all-gather + first-occurrence decisions over the GLOBAL order (:30)
+        t0 = time.perf_counter()
         lib.check(lib.zg_blake3_batch_dev(cx.stream, self.blob.data_ptr(), self.off.data_ptr(), self.ln.data_ptr(), self.n, self.d_dig.data_ptr()))
+        t1 = time.perf_counter()
         first_l, _, first_g, rep_g = self.parallel.global_dedup(lib, self.plan, self.d_dig[: self.n * 32].view(self.n, 32), stream=cx.stream)
+        t2 = time.perf_counter()
         # (3) encode what this rank is first for (:41) -> (4) all-gather of frame sizes, offsets in insertion order (:22,45)
         lib.check(lib.zg_cctx_reset_archive(self.cctx, 0))
         sel = first_l.contiguous()
         lib.check(lib.zg_pack_batch_dev_ex(self.cctx, self.blob.data_ptr(), self.off.data_ptr(), self.ln.data_ptr(), self.n, self.d_dig.data_ptr(),
                                            sel.data_ptr(), None, self.d_first.data_ptr(), self.d_foff.data_ptr(), self.d_flen.data_ptr(),
                                            self.d_frames.data_ptr(), self.cap, self.nbytes.ctypes.data))
+        t3 = time.perf_counter()
         flen_local = self.d_flen[: self.n] * self.d_first[: self.n].to(cx.torch.int64)
         self.g_off, self.g_len, self.total = self.parallel.global_offsets(lib, self.plan, flen_local, first_g, rep_g, base=12, stream=cx.stream)
+        # host-side wall clock of the four parts of a multi-GPU pack (the library calls block until their results are on the host)
+        self.host_ms.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, time.perf_counter()))])
 
     def prepare_unpack(self):
         """After a pack: which files this rank restores (all of them, except duplicates whose only frame another rank holds)."""
@@ -416,6 +423,8 @@ def time_roundtrip(cx: Ctx, rt: RoundTrip, steps: int, warmup: int):
     tp = cx.rank_max(sum(x.elapsed_time(y) for x, y in pk) / steps)
     tu = cx.rank_max(sum(x.elapsed_time(y) for x, y in up) / steps)
     rt.step_ms = {"pack": [round(x.elapsed_time(y), 2) for x, y in pk], "unpack": [round(x.elapsed_time(y), 2) for x, y in up]}
+    if rt.host_ms:
+        rt.step_ms["pack_host_parts[digests,dedup_exchange,encode,offsets_exchange]"] = rt.host_ms[-steps:]
     return total, tp, tu
 
 
@@ -723,6 +732,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     tp = sum(x.elapsed_time(y) for x, y in pack_ms) / args.steps
     tu = sum(x.elapsed_time(y) for x, y in unpack_ms) / args.steps
+    step_ms = {"pack": [round(x.elapsed_time(y), 2) for x, y in pack_ms], "unpack": [round(x.elapsed_time(y), 2) for x, y in unpack_ms]}
+    if rt.host_ms:
+        step_ms["pack_host_parts[digests,dedup_exchange,encode,offsets_exchange]"] = rt.host_ms[-args.steps:]
     total_ms = cx.rank_max(total_ms)
     tp, tu = cx.rank_max(tp), cx.rank_max(tu)
     Btot = cx.rank_sum(float(B))
@@ -731,7 +743,7 @@ def main():
 
     # per-kernel roofline of the dominant kernel (device time from CUDA events on the launching stream)
     prof = {}
-    names = ((0, "k_blake3_small"), (6, "k_zstd_match_blocks"), (7, "k_zstd_literals"), (8, "k_zstd_sequences"), (2, "k_zstd_decode_frames"),
+    names = ((0, "k_blake3_chunks"), (6, "k_zstd_match_blocks"), (7, "k_zstd_literals"), (8, "k_zstd_sequences"), (2, "k_zstd_decode_frames"),
              (1, "encode pass (match+literals+sequences, all chunks)"))
     for k, name in names:
         ms, cnt = C.c_double(0), C.c_uint64(0)
@@ -742,7 +754,7 @@ def main():
     # algorithmic bytes per STEP of each kernel class: the encoder reads the unique input once (match) and
     # writes the compressed bytes once (literals + sequences sections); the decoder reads C and writes N; BLAKE3 reads N
     # (pack digests and unpack verification: two launches per step)
-    alg_step = {"k_blake3_small": 2.0 * B, "k_zstd_match_blocks": uniq_bytes, "k_zstd_literals": C_bytes, "k_zstd_sequences": C_bytes,
+    alg_step = {"k_blake3_chunks": 2.0 * B, "k_zstd_match_blocks": uniq_bytes, "k_zstd_literals": C_bytes, "k_zstd_sequences": C_bytes,
                 "k_zstd_decode_frames": C_bytes + B, "encode pass (match+literals+sequences, all chunks)": uniq_bytes + C_bytes}
     single = [nm for _, nm in names[:5]]
     dom = max(single, key=lambda k: prof[k][0])
@@ -768,10 +780,10 @@ def main():
         try:
             P = json.load(open(ip))
             lane_ops = float(P["int32_lane_ops_per_s"])
-            b3 = kernels["k_blake3_small"]["algorithmic_gbs"]
+            b3 = kernels["k_blake3_chunks"]["algorithmic_gbs"]
             roofline["int_issue"] = {
                 "peak_int32_lane_ops_per_s": lane_ops, "peak_source": P.get("how"),
-                "k_blake3_small": {"bound": "int_issue", "ops_per_byte": 13.1, "ceiling_gbs": lane_ops / 13.1 / 1e9,
+                "k_blake3_chunks": {"bound": "int_issue", "ops_per_byte": 13.1, "ceiling_gbs": lane_ops / 13.1 / 1e9,
                                    "achieved_gbs": b3, "frac": (b3 / (lane_ops / 13.1 / 1e9)) if b3 else None, "hbm_frac": (b3 / peak) if b3 else None},
             }
         except Exception:
@@ -912,7 +924,7 @@ def main():
                        "parallelism": f"files sharded over {world} GPU(s) by {part}; per step: NCCL all-gather of digests (global dedup) and of frame sizes (archive offsets)"
                        if world > 1 else "1 GPU"},
             "pack_gbs": Btot / (tp * 1e-3) / 1e9, "unpack_gbs": Btot / (tu * 1e-3) / 1e9,
-            "ratio": ratio, "ratio_reference_level3": cpu["ratio"] if cpu else None,
+            "ratio": ratio, "ratio_reference_level3": cpu["ratio"] if cpu else None, "rank0_step_ms": step_ms,
             "roofline": roofline,
             "cpu_baseline": ({"value": cpu["value"], "unit": "GB/s", "cores": cores, "kind": "port", "sample": cpu["sample"],
                               "pack_gbs": cpu["pack_gbs"], "unpack_gbs": cpu["unpack_gbs"]} if cpu else None),

@@ -23,6 +23,23 @@ def test_blake3_sizes(emu, shift):
         assert g == blake3.blake3(f).digest(), len(f)
 
 
+@pytest.mark.parametrize("variant", range(13))
+def test_blake3_chunk_kernel_variants(emu, variant):
+    """Every staging / arithmetic variant of the chunk kernel (bulk copies or cp.async, 256- or 512-byte pieces, the
+    additions and rotations of G split over the pipes) gives the same digests."""
+    import blake3
+
+    files = [_data(n, 7) for n in (0, 1, 64, 1000, 1024, 1025, 4096, 5000, 33 * 1024 + 3, 70_001)]
+    emu.dll.zg_internal_set_b3_variant(variant)
+    try:
+        for shift, align in ((0, 1), (3, 1), (0, 16)):
+            got = blake3_batch(emu, files, align=align, shift=shift)
+            for f, g in zip(files, got):
+                assert g == blake3.blake3(f).digest(), (variant, shift, len(f))
+    finally:
+        emu.dll.zg_internal_set_b3_variant(9)
+
+
 def test_blake3_empty_kat(emu):
     assert blake3_batch(emu, [b""])[0].hex() == "af1349b9f5f9a1a6a0404dea36dcc9499bcb25c9adc112b7cc9a93cae41f3262"
 
@@ -30,7 +47,7 @@ def test_blake3_empty_kat(emu):
 def test_blake3_big_file_path(emu):
     import blake3
 
-    # > 1024 chunks goes through the two-pass big-file kernels; mix with small files
+    # a few thousand chunks per file: a dozen tree levels; mixed with small files
     files = [_data(1024 * 1024 + 1), _data(10), _data(1024 * 1024 + 1024 * 33 + 5, 1), _data(2 * 1024 * 1024, 2), b""]
     got = blake3_batch(emu, files, align=16)
     for f, g in zip(files, got):

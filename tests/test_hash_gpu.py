@@ -38,6 +38,25 @@ def test_blake3_many_ragged(gpu):
         assert g == blake3.blake3(f).digest(), len(f)
 
 
+@pytest.mark.parametrize("variant", range(13))
+def test_blake3_chunk_kernel_variants(gpu, variant):
+    from tests import test_hash_emu as cases
+
+    cases.test_blake3_chunk_kernel_variants(gpu, variant)
+    # and a ragged crowd of small files, where groups of 32 chunks straddle many files
+    import blake3
+
+    rng = np.random.default_rng(11 + variant)
+    files = [_data(int(n), 6) for n in rng.integers(0, 40000, 600)]
+    gpu.dll.zg_internal_set_b3_variant(variant)
+    try:
+        got = blake3_batch(gpu, files, shift=variant)
+    finally:
+        gpu.dll.zg_internal_set_b3_variant(9)
+    for f, g in zip(files, got):
+        assert g == blake3.blake3(f).digest(), len(f)
+
+
 @pytest.mark.parametrize("shift", [0, 1, 8])
 def test_xxh64_sizes(gpu, shift):
     import xxhash

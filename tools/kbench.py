@@ -50,6 +50,8 @@ def main():
     args = ap.parse_args()
     lib = product_lib()
     res = {}
+    if os.environ.get("ZG_B3_VARIANT"):  # tuning aid: staging / arithmetic variant of k_blake3_chunks (blake3.cu: b3c_launch)
+        lib.dll.zg_internal_set_b3_variant(int(os.environ["ZG_B3_VARIANT"]))
     c = corpus.c2_source_tree(total_bytes=int(args.gb * 1e9))
     t0 = time.time()
     blob = gen_corpus(lib, c)
@@ -106,6 +108,12 @@ def main():
         dig = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
         best, med = timeit(lambda: lib.check(lib.zg_blake3_batch_dev(s, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, dig.data_ptr())))
         res["blake3_c2_gbs"] = c.total_bytes / best / 1e6
+        if os.environ.get("ZG_B3_SWEEP"):
+            for v in range(13):
+                lib.dll.zg_internal_set_b3_variant(v)
+                best, med = timeit(lambda: lib.check(lib.zg_blake3_batch_dev(s, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, dig.data_ptr())))
+                res[f"blake3_c2_gbs_variant{v}"] = c.total_bytes / best / 1e6
+            lib.dll.zg_internal_set_b3_variant(int(os.environ.get("ZG_B3_VARIANT", "9")))
         c3 = corpus.c3_huge(n_files=4, file_bytes=512 << 20)
         b3 = gen_corpus(lib, c3)
         o3, l3 = dev(c3.off), dev(c3.len)

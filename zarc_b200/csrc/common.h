@@ -68,13 +68,12 @@ struct ZgPerDevice {
 
 // ---- blake3.cu ----
 struct ZgB3Work {
-	ZgBuf big;     // u64 pairs {file idx, len}
-	ZgBuf med;     // u32 indices of files above 64 chunks
-	ZgBuf ucount, ubase, unodes, tiles;  // 8-chunk units of the small files: count / prefix per file, unit nodes, scan scratch
-	ZgBuf ctr;     // u32 counters
-	ZgBuf base;    // u64 group prefix per big file
-	ZgBuf nodes;   // level-5 chaining values of big files
-	ZgHostBuf h;   // pinned staging for the big list
+	ZgBuf cnt, cbase, tiles;  // chunks per file, their exclusive prefix (+ the total), scan scratch
+	ZgBuf meta;               // u64: chunks in all, end of the data, chunks of the largest file
+	ZgBuf taskfile;           // u32 per group of 32 chunks: the file of its first chunk
+	ZgBuf cv0, cv1;           // chaining values: chunks / tree levels (ping-pong)
+	ZgBuf ltab;               // u32 per block of every tree level: the file of its first slot
+	ZgHostBuf h;              // pinned: meta for the host
 };
 size_t zg_blake3_run(cudaStream_t s, ZgB3Work& w, const u8* blob, const u64* off, const u64* len, u64 n, u8* digests);
 void zg_b3work_free(ZgB3Work& w);
