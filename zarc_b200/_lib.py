@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_SO = os.path.join(_HERE, "libzarcgpu.so")
+PRODUCT_SO = os.environ.get("ZARC_B200_LIB") or os.path.join(_HERE, "libzarcgpu.so")  # (the variable: another BUILD of the product library, for tuning runs)
 
 _sz = C.c_size_t
 _vp = C.c_void_p
