@@ -270,10 +270,21 @@ size_t zg_corpus_generate_dev(void* stream, uint8_t* out, const uint64_t* seg_of
 }
 size_t zg_assign_offsets_dev(void* stream, const uint64_t* frame_len, uint64_t n, uint64_t base, uint64_t* frame_off) {
 	ZG_NEED_DEVICE();
-	ZgBuf tiles;
-	size_t r = zg_scan_run((cudaStream_t)stream, tiles, frame_len, n, base, frame_off, nullptr);
+	// (scan scratch kept per device: no cudaMalloc / cudaFree, which synchronise the device, per call)
+	static std::mutex mu;
+	static ZgBuf cache[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) {
+		ZgBuf tiles;
+		size_t r = zg_scan_run((cudaStream_t)stream, tiles, frame_len, n, base, frame_off, nullptr);
+		cudaStreamSynchronize((cudaStream_t)stream);
+		tiles.release();
+		return r;
+	}
+	std::lock_guard<std::mutex> g(mu);
+	size_t r = zg_scan_run((cudaStream_t)stream, cache[dev], frame_len, n, base, frame_off, nullptr);
 	cudaStreamSynchronize((cudaStream_t)stream);
-	tiles.release();
 	return r;
 }
 

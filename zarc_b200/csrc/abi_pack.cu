@@ -1,6 +1,7 @@
 // C ABI, pack side: zg_cctx (CCtx analogue + the Encoder's content state), zg_pack_batch[_dev],
 // zg_compress2.  Host code here only moves buffers and does bookkeeping on counts/sizes.
 #include "common.h"
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -582,18 +583,33 @@ extern "C" size_t zg_dedup_dev(void* stream, const uint8_t* digests, uint64_t n,
 	cudaStream_t s = (cudaStream_t)stream;
 	u64 want = 1024;
 	while (want < 2 * n) want <<= 1;
-	ZgBuf table, tmp;
+	// the table and the scratch are kept per device between calls: cudaMalloc / cudaFree synchronise the whole device,
+	// and beside another process's collectives a cudaFree per call was seen to stall for 0.5-0.8 s now and then
+	struct Scratch {
+		ZgBuf table, tmp;
+	};
+	static std::mutex mu;
+	static Scratch cache[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	Scratch local;
+	const bool cached = dev >= 0 && dev < 64;
+	std::unique_lock<std::mutex> g(mu, std::defer_lock);
+	if (cached) g.lock();
+	Scratch& S = cached ? cache[dev] : local;
 	size_t r = 0;
-	if (table.reserve(want * 4) || tmp.reserve(n * 8 * 4)) r = ZG_ERR(ZG_error_memory_allocation);
+	if (S.table.reserve(want * 4) || S.tmp.reserve(n * 8 * 4)) r = ZG_ERR(ZG_error_memory_allocation);
 	if (!r) {
-		cudaMemsetAsync(table.p, 0, want * 4, s);
-		cudaMemsetAsync(tmp.p, 0, n * 8 * 4, s);
-		u64* t = tmp.as<u64>();
-		r = zg_pk_dedup_insert(s, digests, 0, n, table.as<u32>(), (u32)want - 1);
-		if (!r) r = zg_pk_dedup_resolve(s, digests, 0, n, table.as<u32>(), (u32)want - 1, t, nullptr, rep, first, t + n, t + 2 * n, t + 3 * n);
+		cudaMemsetAsync(S.table.p, 0, want * 4, s);
+		cudaMemsetAsync(S.tmp.p, 0, n * 8 * 4, s);
+		u64* t = S.tmp.as<u64>();
+		r = zg_pk_dedup_insert(s, digests, 0, n, S.table.as<u32>(), (u32)want - 1);
+		if (!r) r = zg_pk_dedup_resolve(s, digests, 0, n, S.table.as<u32>(), (u32)want - 1, t, nullptr, rep, first, t + n, t + 2 * n, t + 3 * n);
 		if (cudaStreamSynchronize(s) != cudaSuccess) r = ZG_ERR(ZG_error_device);
 	}
-	table.release();
-	tmp.release();
+	if (!cached) {
+		local.table.release();
+		local.tmp.release();
+	}
 	return r;
 }
