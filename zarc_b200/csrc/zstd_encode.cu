@@ -445,7 +445,12 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	if (lane == 0) {
 		u32 maxd = 0;
 		ZG_UNROLL1
-		for (u32 limit = 1;; limit <<= 1) {
+		// (a symbol rarer than total / 2^ZS_HUF_MAXLOG would get a longer code than the format allows: start from the
+		// floor that makes such depths unlikely instead of finding it by doubling, one tree build per step)
+		u32 total = 0;
+		ZG_UNROLL1
+		for (u32 i = 0; i < n; i++) total += e.sorted_cnt[i];
+		for (u32 limit = zg_max<u32>(1u, total >> ZS_HUF_MAXLOG);; limit <<= 1) {
 			ZG_UNROLL1
 			for (u32 i = 0; i < n; i++) e.node_cnt[i] = zg_max<u32>(e.sorted_cnt[i], limit);
 			u32 q1 = 0, q2 = n, nn = n;
@@ -1353,6 +1358,9 @@ ZG_DEV u32 ze_sequences_tables(ZeWarp* W, ZePredef* P, const u64* seq, u32* code
 // must have entered its range in the state the lane above left off in; if not (rare) it walks its range again
 // from the right state.  The fields are bit for bit those of the serial walk.  All lanes call; fills M.fin.
 #define ZE_CHAIN_LANES 10u
+#ifndef ZE_CHAIN_AHEAD
+#define ZE_CHAIN_AHEAD 4     // steps whose codes and table rows are fetched before the serial state look-ups of a trip
+#endif
 #define ZE_CHAIN_WARM 96u
 struct ZeChainRun {
 	const u32* codes;
@@ -1361,19 +1369,19 @@ struct ZeChainRun {
 	u16* out;
 	u32 sh;
 };
-// steps from-1 .. to (descending) from `state`; four per trip, the codes and their table rows fetched up front so
+// steps from-1 .. to (descending) from `state`; ZE_CHAIN_AHEAD per trip, the codes and their table rows fetched up front so
 // that only the state look-ups are serial
 ZG_DEV u32 ze_chain_walk(const ZeChainRun& R, u32 state, u32 from, u32 to, bool emit) {
 	u32 i = from;
 	ZG_UNROLL1
 	while (i > to) {
-		u32 m = zg_min<u32>(4u, i - to);
-		ZeSymTT r[4];
+		u32 m = zg_min<u32>((u32)ZE_CHAIN_AHEAD, i - to);
+		ZeSymTT r[ZE_CHAIN_AHEAD];
 		ZG_UNROLL
-		for (u32 k = 0; k < 4; k++)
+		for (u32 k = 0; k < ZE_CHAIN_AHEAD; k++)
 			if (k < m) r[k] = R.tt[(R.codes[i - 1 - k] >> R.sh) & 0xff];
 		ZG_UNROLL
-		for (u32 k = 0; k < 4; k++) {
+		for (u32 k = 0; k < ZE_CHAIN_AHEAD; k++) {
 			if (k < m) {
 				u32 nb = (state + r[k].dnb) >> 16;
 				if (emit) R.out[4 * (i - 1 - k)] = (u16)((state & ((1u << nb) - 1u)) | (nb << 12));
