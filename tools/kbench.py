@@ -50,6 +50,11 @@ def main():
     args = ap.parse_args()
     lib = product_lib()
     res = {}
+    if os.environ.get("ZG_DECODE_BATCHING"):  # tuning aid: "cap_div,min_batch_bytes,floor_bytes" (zstd_decode.cu: the hand-out)
+        import ctypes as C
+
+        a, b, c3 = os.environ["ZG_DECODE_BATCHING"].split(",")
+        lib.dll.zg_internal_set_decode_batching(C.c_uint32(int(a)), C.c_uint32(int(b)), C.c_uint32(int(c3)))
     if os.environ.get("ZG_B3_VARIANT"):  # tuning aid: staging / arithmetic variant of k_blake3_chunks (blake3.cu: b3c_launch)
         lib.dll.zg_internal_set_b3_variant(int(os.environ["ZG_B3_VARIANT"]))
     c = corpus.c2_source_tree(total_bytes=int(args.gb * 1e9))
