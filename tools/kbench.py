@@ -130,6 +130,13 @@ def main():
         h = torch.empty(n, dtype=torch.int64, device="cuda")
         best, med = timeit(lambda: lib.check(lib.zg_xxh64_batch_dev(s, blob.data_ptr(), off.data_ptr(), ln.data_ptr(), n, h.data_ptr())))
         res["xxh64_c2_gbs"] = c.total_bytes / best / 1e6
+        c3 = corpus.c3_huge(n_files=4, file_bytes=512 << 20)
+        b3 = gen_corpus(lib, c3)
+        o3, l3 = dev(c3.off), dev(c3.len)
+        h3 = torch.empty(4, dtype=torch.int64, device="cuda")
+        best, med = timeit(lambda: lib.check(lib.zg_xxh64_batch_dev(s, b3.data_ptr(), o3.data_ptr(), l3.data_ptr(), 4, h3.data_ptr())), iters=3, warmup=1)
+        res["xxh64_c3_gbs_per_file"] = c3.total_bytes / 4 / best / 1e6
+        del b3
     if "decode" in args.what:
         from oracle import ref_path
         import concurrent.futures as cf

@@ -122,7 +122,7 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 // split (each accumulator is a serial multiply-rotate chain over the stripes), but a single thread
 // also pays a memory round trip per 32-byte stripe; here the 32 lanes fetch 1 KiB (32 stripes) at a
 // time, coalesced and one chunk ahead, into shared memory, and lanes 0..3 run one accumulator each
-// from there: the chain's arithmetic latency is all that is left (~2 GB/s per input; many inputs run
+// from there: the chain's arithmetic latency is all that is left (2 GB/s per input; many inputs run
 // side by side).  `sb`: 128 u64 of shared memory per warp.  All lanes call; all lanes get the hash.
 #define XX_WARP_MIN 8192u
 #define XX_PREFETCH_CHUNKS 16u
@@ -131,28 +131,34 @@ ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 	u64 acc = lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;  // seed 0
 	u64 chunks = n >> 10;
 	const u8* q = p + 32 * lane;
-	u64 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+	// The lane's 32 bytes of a chunk as aligned words; they are combined into four u64 (a funnel shift when the input is
+	// not word aligned) only AFTER the chains of the chunk before have run: combined at once, the shifts would wait for
+	// the loads in front of the chains, and every chunk would cost a memory round trip on top of its 32 serial steps.
+	const u32* wq = (const u32*)((uintptr_t)q & ~(uintptr_t)3);
+	const u32 sh = (u32)((uintptr_t)q & 3) * 8;
+	u32 raw[9];
+	ZG_UNROLL
+	for (int k = 0; k < 9; k++) raw[k] = 0;
 	if (chunks) {
-		r0 = zg_ld64(q);
-		r1 = zg_ld64(q + 8);
-		r2 = zg_ld64(q + 16);
-		r3 = zg_ld64(q + 24);
+		ZG_UNROLL
+		for (int k = 0; k < 8; k++) raw[k] = wq[k];
+		if (sh) raw[8] = wq[8];
 	}
 	for (u64 c = 0; c < chunks; c++) {
 		// a warp has one chunk in flight: without help it would stream at one DRAM latency per KiB (measured 1.3 GB/s on a
 		// 4 GiB input).  The lines 16 KiB ahead are asked into L2 now, so that the loads below find them there.
 		if (c + XX_PREFETCH_CHUNKS < chunks) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << 10));
-		sb[4 * lane + 0] = r0 * XXP2;  // the products are off the chain: all 32 lanes make them
-		sb[4 * lane + 1] = r1 * XXP2;
-		sb[4 * lane + 2] = r2 * XXP2;
-		sb[4 * lane + 3] = r3 * XXP2;
+		ZG_UNROLL
+		for (int j = 0; j < 4; j++) {  // the products are off the chain: all 32 lanes make them
+			u64 r = ((u64)__funnelshift_r(raw[2 * j + 1], raw[2 * j + 2], sh) << 32) | __funnelshift_r(raw[2 * j], raw[2 * j + 1], sh);
+			sb[4 * lane + j] = r * XXP2;
+		}
 		__syncwarp();
 		if (c + 1 < chunks) {  // in flight while the chains run
-			const u8* qn = q + ((c + 1) << 10);
-			r0 = zg_ld64(qn);
-			r1 = zg_ld64(qn + 8);
-			r2 = zg_ld64(qn + 16);
-			r3 = zg_ld64(qn + 24);
+			const u32* wn = wq + ((c + 1) << 8);
+			ZG_UNROLL
+			for (int k = 0; k < 8; k++) raw[k] = wn[k];
+			if (sh) raw[8] = wn[8];
 		}
 		if (lane < 4) {
 			// b = acc + x0, then 32 steps each absorbing the next stripe's x (the last one absorbs 0: b becomes acc)
