@@ -442,134 +442,178 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 		e.sorted_sym[rank] = (u16)(key & 0xff);
 	}
 	__syncwarp();
-	if (lane == 0) {
-		u32 maxd = 0;
-		ZG_UNROLL1
-		// (a symbol rarer than total / 2^ZS_HUF_MAXLOG would get a longer code than the format allows: start from the
-		// floor that makes such depths unlikely instead of finding it by doubling, one tree build per step)
-		u32 total = 0;
-		ZG_UNROLL1
-		for (u32 i = 0; i < n; i++) total += e.sorted_cnt[i];
-		for (u32 limit = zg_max<u32>(1u, total >> ZS_HUF_MAXLOG);; limit <<= 1) {
-			ZG_UNROLL1
-			for (u32 i = 0; i < n; i++) e.node_cnt[i] = zg_max<u32>(e.sorted_cnt[i], limit);
+	// The tree.  Only the merge of the two sorted queues is serial (lane 0, the queue heads' counts kept in registers);
+	// the leaves' depths (every leaf walks to the root), the weights, their histogram and the canonical codes are
+	// lane-parallel.  Same tree, weights and codes as the serial construction.
+	u32 total = 0;
+	for (u32 i = lane; i < n; i += 32) total += e.sorted_cnt[i];
+	total = zg_warp_sum(total);
+	const u32 root = 2 * n - 2;
+	u32 maxd = 0;
+	// (a symbol rarer than total / 2^ZS_HUF_MAXLOG would get a longer code than the format allows: start from the
+	// floor that makes such depths unlikely instead of finding it by doubling, one tree build per step)
+	ZG_UNROLL1
+	for (u32 limit = zg_max<u32>(1u, total >> ZS_HUF_MAXLOG);; limit <<= 1) {
+		for (u32 i = lane; i < n; i += 32) e.node_cnt[i] = zg_max<u32>(e.sorted_cnt[i], limit);
+		__syncwarp();
+		if (lane == 0) {
 			u32 q1 = 0, q2 = n, nn = n;
+			u32 c1 = e.node_cnt[0], c2 = 0xffffffffu;  // heads of the leaf queue and of the internal-node queue
 			ZG_UNROLL1
 			while (nn < 2 * n - 1) {
-				u32 a, b;
-				if (q1 < n && (q2 >= nn || e.node_cnt[q1] <= e.node_cnt[q2])) a = q1++;
-				else a = q2++;
-				if (q1 < n && (q2 >= nn || e.node_cnt[q1] <= e.node_cnt[q2])) b = q1++;
-				else b = q2++;
-				e.node_cnt[nn] = e.node_cnt[a] + e.node_cnt[b];
+				u32 a, b, ca, cb;
+				if (q1 < n && (q2 >= nn || c1 <= c2)) {
+					a = q1++;
+					ca = c1;
+					c1 = q1 < n ? e.node_cnt[q1] : 0xffffffffu;
+				} else {
+					a = q2++;
+					ca = c2;
+					c2 = q2 < nn ? e.node_cnt[q2] : 0xffffffffu;
+				}
+				if (q1 < n && (q2 >= nn || c1 <= c2)) {
+					b = q1++;
+					cb = c1;
+					c1 = q1 < n ? e.node_cnt[q1] : 0xffffffffu;
+				} else {
+					b = q2++;
+					cb = c2;
+					c2 = q2 < nn ? e.node_cnt[q2] : 0xffffffffu;
+				}
+				u32 sum = ca + cb;
+				e.node_cnt[nn] = sum;
+				if (q2 == nn) c2 = sum;  // the internal queue was empty: the new node is its head
 				e.node_par[a] = (u16)nn;
 				e.node_par[b] = (u16)nn;
 				nn++;
 			}
-			e.node_depth[2 * n - 2] = 0;
-			maxd = 0;
+		}
+		__syncwarp();
+		u32 md = 0;
+		for (u32 i = lane; i < n; i += 32) {
+			u32 d = 0, k = i;
 			ZG_UNROLL1
-			for (i32 k = (i32)(2 * n - 3); k >= 0; k--) {
-				u32 d = e.node_depth[e.node_par[k]] + 1u;
-				e.node_depth[k] = (u8)d;
-				if ((u32)k < n && d > maxd) maxd = d;
+			while (k != root) {
+				k = e.node_par[k];
+				d++;
 			}
-			if (maxd <= ZS_HUF_MAXLOG) break;
+			e.node_depth[i] = (u8)d;
+			md = zg_max<u32>(md, d);
 		}
-		// weights and canonical codes (ascending weight, then ascending symbol: RFC 8878 §4.2.1)
-		u32 rank[13];
-		ZG_UNROLL1
-		for (u32 w = 0; w < 13; w++) rank[w] = 0;
-		ZG_UNROLL1
-		for (u32 i = 0; i < n; i++) {
-			u32 w = maxd + 1 - e.node_depth[i];
-			e.hweight[e.sorted_sym[i]] = (u8)w;
-			rank[w]++;
-		}
-		u32 next[13];
+		maxd = zg_warp_max(md);
+		__syncwarp();
+		if (maxd <= ZS_HUF_MAXLOG) break;
+	}
+	// weights and canonical codes (ascending weight, then ascending symbol: RFC 8878 §4.2.1)
+	u32* rk = W->hist;       // [0..12] symbols per weight (the literal histogram has been consumed)
+	u32* nx = W->hist + 16;  // [1..12] next code of each weight
+	if (lane < 13) rk[lane] = 0;
+	__syncwarp();
+	for (u32 i = lane; i < n; i += 32) {
+		u32 w = maxd + 1 - e.node_depth[i];
+		e.hweight[e.sorted_sym[i]] = (u8)w;
+		atomicAdd(&rk[w], 1u);
+	}
+	__syncwarp();
+	if (lane == 0) {
 		u32 start = 0;
 		ZG_UNROLL1
 		for (u32 w = 1; w <= maxd; w++) {
-			next[w] = start >> (w - 1);
-			start += rank[w] << (w - 1);
-		}
-		ZG_UNROLL1
-		for (u32 s = 0; s <= maxsym; s++) {
-			u32 w = e.hweight[s];
-			if (w) {
-				u32 nb = maxd + 1 - w;
-				e.hcode[s] = (u16)(next[w]++ | (nb << 11));
-			}
+			nx[w] = start >> (w - 1);
+			start += rk[w] << (w - 1);
 		}
 		W->misc[0] = maxd;
+	}
+	__syncwarp();
+	for (u32 s0 = 0; s0 <= maxsym; s0 += 32) {
+		u32 sy = s0 + lane;
+		u32 w = sy <= maxsym ? e.hweight[sy] : 0u;
+		u32 peers = __match_any_sync(ZG_FULL, w);
+		u32 base = w ? nx[w] : 0u;
+		__syncwarp();
+		if (w) {
+			e.hcode[sy] = (u16)((base + (u32)__popc(peers & zg_lanemask_lt())) | ((maxd + 1 - w) << 11));
+			if ((peers & zg_lanemask_lt()) == 0) nx[w] = base + (u32)__popc(peers);
+		}
+		__syncwarp();
 	}
 	__syncwarp();
 	*maxsym_out = maxsym;
 	return W->misc[0];
 }
 
-// Huffman tree description into e.wdesc (single lane).  Returns its size, 0 if not representable.
+// Huffman tree description into e.wdesc.  Returns its size, 0 if not representable.  All lanes call: the histogram of
+// the weights and the FSE table are built by the warp; the FSE stream itself (two interleaved states over <= 255
+// weights) is a serial chain and stays with lane 0.
 ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 	ZeEnt& e = W->e;
+	u32 lane = zg_lane();
 	u32 nw = maxsym;  // weights 0..maxsym-1 are explicit, the last is implied
 	u32 direct = nw <= 128 ? 1 + ((nw + 1) >> 1) : 0;
 	u32 fse_size = 0;
 	if (nw > 2) {
-		u32 cnt[13];
-		ZG_UNROLL1
-		for (u32 i = 0; i < 13; i++) cnt[i] = 0;
-		u32 maxw = 0, maxc = 0;
-		ZG_UNROLL1
-		for (u32 i = 0; i < nw; i++) {
-			u32 w = e.hweight[i];
-			cnt[w]++;
-			if (w > maxw) maxw = w;
-		}
-		ZG_UNROLL1
-		for (u32 i = 0; i <= maxw; i++) maxc = zg_max<u32>(maxc, cnt[i]);
+		u32* cnt = W->hist + 32;  // [13] (scratch: the literal histogram has been consumed)
+		if (lane < 13) cnt[lane] = 0;
+		__syncwarp();
+		for (u32 i = lane; i < nw; i += 32) atomicAdd(&cnt[e.hweight[i]], 1u);
+		__syncwarp();
+		u32 c = lane < 13 ? cnt[lane] : 0u;
+		u32 maxw = 31u - (u32)__clz((int)(__ballot_sync(ZG_FULL, c > 0) | 1u));
+		u32 maxc = zg_warp_max(c);
 		if (maxc != nw && maxc > 1) {
 			u32 log = ze_fse_table_log(6, nw, maxw);
-			ze_fse_normalize(e.norm, cnt, nw, maxw, log);
-			u32 nc = ze_fse_write_ncount(e.wdesc + 1, 127, e.norm, maxw, log);
+			if (lane == 0) {
+				ze_fse_normalize(e.norm, cnt, nw, maxw, log);
+				W->misc[2] = ze_fse_write_ncount(e.wdesc + 1, 127, e.norm, maxw, log);
+			}
+			__syncwarp();
+			u32 nc = W->misc[2];
 			if (nc) {
 				ZeCT ct{e.st[2], e.tt[2], log};
-				ze_fse_build_ctable(ct, e.norm, maxw, e.tsym, e.cumul);
-				ZeBitW bw;
-				ze_bw_init(bw, e.wdesc + 1 + nc, e.wdesc + 128);
-				u32 ip = nw, s1, s2;
-				// libzstd FSE_compress_usingCTable order: the last two weights seed the two states
-				if (nw & 1) {
-					s1 = ze_fse_init_state(ct, e.hweight[--ip]);
-					s2 = ze_fse_init_state(ct, e.hweight[--ip]);
-					ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
-				} else {
-					s2 = ze_fse_init_state(ct, e.hweight[--ip]);
-					s1 = ze_fse_init_state(ct, e.hweight[--ip]);
+				ze_fse_build_ctable_warp(ct, e.norm, maxw, e.tsym, e.cumul);
+				__syncwarp();
+				if (lane == 0) {
+					ZeBitW bw;
+					ze_bw_init(bw, e.wdesc + 1 + nc, e.wdesc + 128);
+					u32 ip = nw, s1, s2;
+					// libzstd FSE_compress_usingCTable order: the last two weights seed the two states
+					if (nw & 1) {
+						s1 = ze_fse_init_state(ct, e.hweight[--ip]);
+						s2 = ze_fse_init_state(ct, e.hweight[--ip]);
+						ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
+					} else {
+						s2 = ze_fse_init_state(ct, e.hweight[--ip]);
+						s1 = ze_fse_init_state(ct, e.hweight[--ip]);
+					}
+					ZG_UNROLL1
+					while (ip > 0) {
+						ze_fse_encode(bw, ct, s2, e.hweight[--ip]);
+						ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
+					}
+					ze_fse_flush_state(bw, ct, s2);
+					ze_fse_flush_state(bw, ct, s1);
+					u8* endp = ze_bw_close(bw);
+					u32 csz = (u32)(endp - (e.wdesc + 1));
+					W->misc[2] = (!bw.ovf && csz < 128) ? 1 + csz : 0;
 				}
-				ZG_UNROLL1
-				while (ip > 0) {
-					ze_fse_encode(bw, ct, s2, e.hweight[--ip]);
-					ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
-				}
-				ze_fse_flush_state(bw, ct, s2);
-				ze_fse_flush_state(bw, ct, s1);
-				u8* endp = ze_bw_close(bw);
-				u32 csz = (u32)(endp - (e.wdesc + 1));
-				if (!bw.ovf && csz < 128) fse_size = 1 + csz;
+				__syncwarp();
+				fse_size = W->misc[2];
 			}
+			__syncwarp();
 		}
 	}
 	if (fse_size && (direct == 0 || fse_size < direct)) {
-		e.wdesc[0] = (u8)(fse_size - 1);
+		if (lane == 0) e.wdesc[0] = (u8)(fse_size - 1);
+		__syncwarp();
 		return fse_size;
 	}
 	if (!direct) return 0;
-	e.wdesc[0] = (u8)(127 + nw);
-	ZG_UNROLL1
-	for (u32 i = 0; i < nw; i += 2) {
+	if (lane == 0) e.wdesc[0] = (u8)(127 + nw);
+	for (u32 i = 2 * lane; i < nw; i += 64) {
 		u32 hi = e.hweight[i], lo = i + 1 < nw ? e.hweight[i + 1] : 0;
 		e.wdesc[1 + (i >> 1)] = (u8)((hi << 4) | lo);
 	}
+	__syncwarp();
 	return direct;
 }
 
@@ -1185,10 +1229,7 @@ ZG_DEV u32 ze_literals_section(ZeWarp* W, const u8* lit, u32 nlit, u8* dst, u32 
 	} else if (nlit >= 64) {
 		maxbits = ze_huf_build(W, &maxsym);
 		if (maxbits) {
-			if (lane == 0) W->misc[1] = ze_huf_write_tree(W, maxsym);
-			__syncwarp();
-			tree = W->misc[1];
-			__syncwarp();
+			tree = ze_huf_write_tree(W, maxsym);
 		}
 		if (tree) {
 			if (streams == 1) {
