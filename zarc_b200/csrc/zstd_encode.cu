@@ -446,6 +446,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	// the leaves' depths (every leaf walks to the root), the weights, their histogram and the canonical codes are
 	// lane-parallel.  Same tree, weights and codes as the serial construction.
 	u32 total = 0;
+	ZG_UNROLL1
 	for (u32 i = lane; i < n; i += 32) total += e.sorted_cnt[i];
 	total = zg_warp_sum(total);
 	const u32 root = 2 * n - 2;
@@ -454,6 +455,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	// floor that makes such depths unlikely instead of finding it by doubling, one tree build per step)
 	ZG_UNROLL1
 	for (u32 limit = zg_max<u32>(1u, total >> ZS_HUF_MAXLOG);; limit <<= 1) {
+		ZG_UNROLL1
 		for (u32 i = lane; i < n; i += 32) e.node_cnt[i] = zg_max<u32>(e.sorted_cnt[i], limit);
 		__syncwarp();
 		if (lane == 0) {
@@ -490,6 +492,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 		}
 		__syncwarp();
 		u32 md = 0;
+		ZG_UNROLL1
 		for (u32 i = lane; i < n; i += 32) {
 			u32 d = 0, k = i;
 			ZG_UNROLL1
@@ -509,6 +512,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 	u32* nx = W->hist + 16;  // [1..12] next code of each weight
 	if (lane < 13) rk[lane] = 0;
 	__syncwarp();
+	ZG_UNROLL1
 	for (u32 i = lane; i < n; i += 32) {
 		u32 w = maxd + 1 - e.node_depth[i];
 		e.hweight[e.sorted_sym[i]] = (u8)w;
@@ -525,6 +529,7 @@ ZG_DEV_NOINLINE u32 ze_huf_build(ZeWarp* W, u32* maxsym_out) {
 		W->misc[0] = maxd;
 	}
 	__syncwarp();
+	ZG_UNROLL1
 	for (u32 s0 = 0; s0 <= maxsym; s0 += 32) {
 		u32 sy = s0 + lane;
 		u32 w = sy <= maxsym ? e.hweight[sy] : 0u;
@@ -555,6 +560,7 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 		u32* cnt = W->hist + 32;  // [13] (scratch: the literal histogram has been consumed)
 		if (lane < 13) cnt[lane] = 0;
 		__syncwarp();
+		ZG_UNROLL1
 		for (u32 i = lane; i < nw; i += 32) atomicAdd(&cnt[e.hweight[i]], 1u);
 		__syncwarp();
 		u32 c = lane < 13 ? cnt[lane] : 0u;
@@ -609,6 +615,7 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 	}
 	if (!direct) return 0;
 	if (lane == 0) e.wdesc[0] = (u8)(127 + nw);
+	ZG_UNROLL1
 	for (u32 i = 2 * lane; i < nw; i += 64) {
 		u32 hi = e.hweight[i], lo = i + 1 < nw ? e.hweight[i + 1] : 0;
 		e.wdesc[1 + (i >> 1)] = (u8)((hi << 4) | lo);
