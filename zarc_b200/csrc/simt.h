@@ -62,16 +62,9 @@ ZG_DEV u32 zg_warp_incl_scan(u32 v) {
 	}
 	return v;
 }
-ZG_DEV u32 zg_warp_sum(u32 v) {
-	ZG_UNROLL
-	for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(ZG_FULL, v, d);
-	return v;
-}
-ZG_DEV u32 zg_warp_max(u32 v) {
-	ZG_UNROLL
-	for (int d = 16; d > 0; d >>= 1) v = zg_max(v, __shfl_xor_sync(ZG_FULL, v, d));
-	return v;
-}
+// warp-wide sum / maximum of one u32 per lane: the hardware's one-instruction reduction (REDUX)
+ZG_DEV u32 zg_warp_sum(u32 v) { return __reduce_add_sync(ZG_FULL, v); }
+ZG_DEV u32 zg_warp_max(u32 v) { return __reduce_max_sync(ZG_FULL, v); }
 
 // unaligned little-endian loads (global or shared)
 ZG_DEV u32 zg_ld16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }
