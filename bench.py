@@ -775,6 +775,15 @@ def main():
                 "note": "integer/latency-bound kernels (bitstream decode, match finding, entropy coding); the HBM roofline is the "
                         "ceiling the north star names for decode and verify; BLAKE3 and match finding are bound by INT32 issue "
                         "(int_issue below: this repo's measured INT32 peak, tools/kbench.py --what intpeak)"}
+    isp = os.path.join(ROOT, "profiles", "ncu_issue.json")
+    if os.path.exists(isp):
+        try:
+            I = json.load(open(isp))
+            roofline["issue"] = {"what": "issue-slot utilisation of the hot kernels from the committed ncu captures: the ceiling that applies to the "
+                                         "latency-bound kernels (match finding, entropy coding, decoding)",
+                                 **{k: v for k, v in I.items() if not k.startswith("_")}}
+        except Exception:
+            pass
     ip = os.path.join(ROOT, "profiles", "int_peak.json")
     if os.path.exists(ip):
         try:
