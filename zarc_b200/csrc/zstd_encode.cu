@@ -864,7 +864,7 @@ ZG_DEV void ze_ld128(const u8* p, const u8* lim, u32 out[4]) {
 	u32 sh = (u32)(a & 3) * 8;
 	u32 x[5];
 	ZG_UNROLL
-	for (int k = 0; k < 5; k++) x[k] = (const u8*)(w + k) < lim ? w[k] : 0u;
+	for (int k = 0; k < 5; k++) x[k] = (const u8*)(w + k) < lim ? __ldg(w + k) : 0u;  // (the input is read-only for the whole kernel: global, non-coherent loads)
 	ZG_UNROLL
 	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
 }
@@ -877,8 +877,8 @@ ZG_DEV u32 ze_ld128_prev(const u8* p, const u8* lo, const u8* lim, u32 out[4]) {
 	u32 sh = (u32)(a & 3) * 8;
 	u32 x[5];
 	ZG_UNROLL
-	for (int k = 0; k < 5; k++) x[k] = (!GUARD || (const u8*)(w + k) < lim) ? w[k] : 0u;
-	u32 xm = (p >= lo + 4 && (!GUARD || (const u8*)(w - 1) < lim)) ? w[-1] : 0u;
+	for (int k = 0; k < 5; k++) x[k] = (!GUARD || (const u8*)(w + k) < lim) ? __ldg(w + k) : 0u;
+	u32 xm = (p >= lo + 4 && (!GUARD || (const u8*)(w - 1) < lim)) ? __ldg(w - 1) : 0u;
 	ZG_UNROLL
 	for (int k = 0; k < 4; k++) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
 	return __funnelshift_r(xm, x[0], sh);
