@@ -16,6 +16,7 @@ static inline void zg_emu_launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t s
 #define ZG_UNROLL
 #define ZG_CONST_TABLE static const
 #define zg_prefetch_l2(p) ((void)(p))
+#define zg_prefetch_l1(p) ((void)(p))
 #else
 #include <cuda_runtime.h>
 #define ZG_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; type* name = (type*)name##_raw_
@@ -23,6 +24,7 @@ static inline void zg_emu_launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t s
 #define ZG_UNROLL _Pragma("unroll")
 #define ZG_CONST_TABLE static __device__ const
 #define zg_prefetch_l2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define zg_prefetch_l1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #endif
 
 #define ZG_DEV __device__ __forceinline__

@@ -1361,6 +1361,7 @@ ZG_DEV u32 ze_sequences_tables(ZeWarp* W, ZePredef* P, const u64* seq, u32* code
 	for (u32 i = lane; i < nseq; i += 32) {
 		u64 q = q_next;
 		q_next = i + 32 < nseq ? seq[i + 32] : 0;
+		if (i + 128 < nseq) zg_prefetch_l1(seq + i + 128);
 		u32 lc = ze_ll_code(ZE_SEQ_LL(q)), mc = ze_ml_code(ZE_SEQ_ML(q) - 3), oc = zs_highbit(ZE_SEQ_OF(q));
 		codes[i] = lc | (mc << 8) | (oc << 16);
 		atomicAdd(&e.hist3[0][lc], 1u);
@@ -1423,6 +1424,7 @@ ZG_DEV u32 ze_chain_walk(const ZeChainRun& R, u32 state, u32 from, u32 to, bool 
 	u32 i = from;
 	ZG_UNROLL1
 	while (i > to) {
+		zg_prefetch_l1(R.codes + (i > 48u ? i - 48u : 0u));  // the walk runs down the codes: the sector a dozen trips on
 		u32 m = zg_min<u32>((u32)ZE_CHAIN_AHEAD, i - to);
 		ZeSymTT r[ZE_CHAIN_AHEAD];
 		ZG_UNROLL
@@ -1543,6 +1545,10 @@ ZG_DEV u32 ze_sequences_pack(ZeWarp* W, const u64* seq, const u32* codes, const 
 			c_next = codes[i];
 			sb_next = stb[i];
 			q_next = seq[i];
+			if (i >= 96) {  // and the lines three trips further down are asked into L1
+				zg_prefetch_l1(stb + i - 96);
+				zg_prefetch_l1(seq + i - 96);
+			}
 		}
 		if (lane < hi) {
 			u32 lc = c & 0xff, mc = (c >> 8) & 0xff, oc = c >> 16;
