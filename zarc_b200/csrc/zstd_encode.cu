@@ -632,6 +632,7 @@ ZG_DEV_NOINLINE u32 ze_huf_count_bits(const ZeEnt& e, const u8* lit, u32 m) {
 	for (u32 i = lane; i < m; i += 32) {
 		u32 b = b_next;
 		b_next = i + 32 < m ? lit[i + 32] : 0u;
+		if (i + 256 < m) zg_prefetch_l1(lit + i + 256);
 		bits += e.hcode[b] >> 11;
 	}
 	return zg_warp_sum(bits);
@@ -650,6 +651,7 @@ ZG_DEV_NOINLINE void ze_huf_encode_stream(ZeWarp* W, const u8* lit, u32 m, u8* d
 	// chunks of 32 lanes x 4 literals, walking from the end of the segment
 	for (u32 done = 0; done < m || done == 0; done += 128) {
 		// lane handles literals at reverse indices r = done + 4*lane + k  (r = 0 is the last literal)
+		if (done + 256 + 4 * lane < m) zg_prefetch_l1(lit + (m - 1 - (done + 256 + 4 * lane)));  // two trips ahead
 		u64 acc = 0;
 		u32 nb = 0;
 		for (u32 k = 0; k < 4; k++) {
@@ -1212,6 +1214,7 @@ ZG_DEV u32 ze_literals_section(ZeWarp* W, const u8* lit, u32 nlit, u8* dst, u32 
 		u32 i = i0 + 4 * lane;
 		u32 w = w_next;
 		w_next = i + 132 <= nlit ? *(const u32*)(lit + i + 128) : 0u;  // the literal buffer of a block is 16-byte aligned
+		if (i + 512 < nlit) zg_prefetch_l1(lit + i + 512);
 		if (i + 4 <= nlit) {
 			atomicAdd(&W->hist[w & 0xff], 1u);
 			atomicAdd(&W->hist[(w >> 8) & 0xff], 1u);
