@@ -30,6 +30,9 @@
 // The uniform per-block helpers (table builds, literals, warp copies) are kept OUT OF LINE on purpose: inlined,
 // the kernel was 207 KB of code with 700 B of spills and 12 % slower.
 #include "zstd_decode.cuh"
+#ifndef ZD_B_STEPS
+#define ZD_B_STEPS 64   // sequences a lane decodes before the warp reconverges (phase B)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Frames are handed to the warps in descending order of compressed size (counting sort), so that the
@@ -177,7 +180,7 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 				const u32* mlt = (L.flags & ZD_F_ML_DEF) ? ZS_ML_DEFAULT_DTABLE : my_slot + 512;
 				const u32* oft = (L.flags & ZD_F_OF_DEF) ? ZS_OF_DEFAULT_DTABLE : my_slot + 1024;
 				for (;;) {
-					u32 cnt = zg_min<u32>(64u, L.nseq_left);
+					u32 cnt = zg_min<u32>((u32)ZD_B_STEPS, L.nseq_left);
 					if (!__any_sync(ZG_FULL, cnt > 0)) break;
 					if (cnt && !zd_lane_decode(L, cnt, llt, mlt, oft, arena + L.seq_base + (L.nseq - L.nseq_left))) zd_fail(L, ZS_E_CORRUPT);
 				}

@@ -794,7 +794,9 @@ ZG_DEV void zd_lane_overlap(u8* d, u32 off, u32 ml) {
 	}
 }
 
+#ifndef ZD_LANE_COPY_MAX
 #define ZD_LANE_COPY_MAX 64u   // longer literal runs / matches are copied by the whole warp
+#endif
 
 // Phase C: execute `cnt` (<= 32) sequences, one per lane.  Output and literal positions come from
 // warp scans.  All literal runs are independent and copied first, lane-parallel.  Matches then go in

@@ -53,7 +53,9 @@
 #ifndef ZE_OF_LOGCAP
 #define ZE_OF_LOGCAP (ZS_OF_MAXLOG - 1)
 #endif
+#ifndef ZE_LANE_CAP
 #define ZE_LANE_CAP 64u   // per-lane match extension cap; longer matches are extended by the whole warp
+#endif
 #define ZE_RAW 0x80000000u
 
 ZG_CONST_TABLE u8 ZS_LL_CODE[64] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 20, 20, 21, 21, 21, 21, 22, 22, 22, 22, 22, 22, 22, 22, 23, 23, 23, 23, 23, 23, 23, 23, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24, 24};
