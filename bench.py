@@ -218,12 +218,18 @@ def measured_peaks():
     return hbm, src
 
 
-def ncu_traffic(kernel: str):
-    """DRAM bytes per launch from the committed `ncu --set full` capture of this workload, or None."""
+def ncu_traffic(kernel: str, input_bytes_per_launch: float | None = None):
+    """DRAM bytes per launch from the committed `ncu --set full` capture of this kernel, or None.  The capture names the
+    input bytes of ITS launch (`corpus_bytes`); a launch of this run that covers a different amount of input (the encoder
+    works in chunks) is charged in proportion."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+            e = json.load(open(p)).get(kernel, {})
+            t = e.get("dram_bytes_per_launch")
+            if t and input_bytes_per_launch and e.get("corpus_bytes"):
+                t = t * input_bytes_per_launch / e["corpus_bytes"]
+            return t
         except Exception:
             return None
     return None
@@ -770,7 +776,7 @@ def main():
     alg_launch = alg_step[dom] / lps
     achieved = alg_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "traffic": ncu_traffic(dom, (uniq_bytes if dom != "k_zstd_decode_frames" else float(B)) / lps), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_launch, "kernels": kernels,
                 "note": "integer/latency-bound kernels (bitstream decode, match finding, entropy coding); the HBM roofline is the "
                         "ceiling the north star names for decode and verify; BLAKE3 and match finding are bound by INT32 issue "

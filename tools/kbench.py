@@ -55,6 +55,10 @@ def main():
 
         a, b, c3 = os.environ["ZG_DECODE_BATCHING"].split(",")
         lib.dll.zg_internal_set_decode_batching(C.c_uint32(int(a)), C.c_uint32(int(b)), C.c_uint32(int(c3)))
+    if os.environ.get("ZG_ENC_CHUNK_MB"):  # tuning aid: input bytes per encoder chunk (zstd_encode.cu)
+        import ctypes as C
+
+        lib.dll.zg_internal_set_encode_chunk_bytes(C.c_uint64(int(os.environ["ZG_ENC_CHUNK_MB"]) << 20))
     if os.environ.get("ZG_B3_VARIANT"):  # tuning aid: staging / arithmetic variant of k_blake3_chunks (blake3.cu: b3c_launch)
         lib.dll.zg_internal_set_b3_variant(int(os.environ["ZG_B3_VARIANT"]))
     c = corpus.c2_source_tree(total_bytes=int(args.gb * 1e9))

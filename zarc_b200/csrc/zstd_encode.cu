@@ -36,7 +36,7 @@
 #define ZE_ENT_CTAS 6   // K3a/K3b: CTAs per SM
 #endif
 #ifndef ZE_CHUNK_BYTES
-#define ZE_CHUNK_BYTES (1ull << 30)  // input bytes per chunk (staging between the kernels = 6x this)
+#define ZE_CHUNK_BYTES (2ull << 30)  // input bytes per chunk (staging between the kernels = 6x this); 0.25 / 0.5 / 1 / 2 / 4 GiB: 47.0 / 49.8 / 50.1 / 50.8 / 51.0 GB/s pack
 #endif
 #define ZE_NQ 4  // queue counters per chunk (one per kernel)
 #define ZE_MAXSEQ 32768u
