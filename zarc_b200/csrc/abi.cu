@@ -123,9 +123,6 @@ struct zg_dctx {
 		cudaEvent_t in_done = nullptr, out_done = nullptr;
 	} hstage[2];
 	cudaStream_t s_in = nullptr, s_out = nullptr;
-	cudaStream_t s_side = nullptr;   // checksum check beside BLAKE3 verification (unpack_core)
-	cudaEvent_t side_fork = nullptr, side_join = nullptr;
-	bool side_init = false;
 	ZgBuf d_archive, d_out, d_meta;  // one-shot / streaming paths
 	ZgHostBuf h_first, h_small;
 	// streaming state (zg_decompress_stream): the frame is collected and decoded ON THE DEVICE; the host keeps only
@@ -172,34 +169,15 @@ static size_t unpack_core(zg_dctx* d, const u8* archive, u64 archive_len, u64 n,
 	}
 	ZG_TRY(zg_zstd_decode_run(s, d->zd, archive, archive_len, off, len, ulen, out_off, n, out, out_cap, st, d->produced.as<u64>(),
 	                          d->cksums.as<u32>()));
+	ZG_TRY(zg_unpack_finalize_run(s, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum));
 	if (digests && ok) {
 		ZG_ALLOC(d->got_digests.reserve(n * 32));
 		ZG_ALLOC(d->vspan.reserve(n * 16));
 		// only frames that decoded are hashed: a rejected frame's output span may lie outside `out`
 		u64* voff = d->vspan.as<u64>();
 		ZG_TRY(zg_verify_spans_run(s, st, out_off, ulen, out_cap, n, voff, voff + n));
-		// the size / Content_Checksum check (XXH64: a few lanes per frame, latency-bound) runs on a side stream beside
-		// BLAKE3 (ALU-bound): both only read the decoded bytes; the digest comparison waits for both
-		if (!d->side_init) {
-			d->side_init = true;
-			if (cudaStreamCreateWithFlags(&d->s_side, cudaStreamNonBlocking) != cudaSuccess ||
-			    cudaEventCreateWithFlags(&d->side_fork, cudaEventDisableTiming) != cudaSuccess ||
-			    cudaEventCreateWithFlags(&d->side_join, cudaEventDisableTiming) != cudaSuccess)
-				d->s_side = nullptr;
-		}
-		cudaStream_t sf = d->s_side ? d->s_side : s;
-		if (d->s_side) {
-			ZG_CUDA(cudaEventRecord(d->side_fork, s));
-			ZG_CUDA(cudaStreamWaitEvent(d->s_side, d->side_fork, 0));
-		}
-		ZG_TRY(zg_unpack_finalize_run(sf, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum));
-		if (d->s_side) ZG_CUDA(cudaEventRecord(d->side_join, d->s_side));
-		size_t rb = zg_blake3_run(s, d->b3, out, voff, voff + n, n, d->got_digests.as<u8>());
-		if (d->s_side) ZG_CUDA(cudaStreamWaitEvent(s, d->side_join, 0));  // (joined whatever BLAKE3 returned)
-		ZG_TRY(rb);
+		ZG_TRY(zg_blake3_run(s, d->b3, out, voff, voff + n, n, d->got_digests.as<u8>()));
 		ZG_TRY(zg_digest_compare_run(s, d->got_digests.as<u8>(), digests, st, ok, n));
-	} else {
-		ZG_TRY(zg_unpack_finalize_run(s, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum));
 	}
 	ZG_TRY(zg_first_error_run(s, st, n, d->first.as<u64>()));
 	u64* hf = d->h_first.as<u64>();
@@ -446,9 +424,6 @@ void zg_dctx_free(zg_dctx* d) {
 	}
 	if (d->s_in) cudaStreamDestroy(d->s_in);
 	if (d->s_out) cudaStreamDestroy(d->s_out);
-	if (d->s_side) cudaStreamDestroy(d->s_side);
-	if (d->side_fork) cudaEventDestroy(d->side_fork);
-	if (d->side_join) cudaEventDestroy(d->side_join);
 	d->h_first.release();
 	d->h_small.release();
 	if (d->own_stream) cudaStreamDestroy(d->stream);
