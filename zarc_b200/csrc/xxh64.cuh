@@ -126,7 +126,9 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 // side by side).  `sb`: 128 u64 of shared memory per warp.  All lanes call; all lanes get the hash.
 #define XX_WARP_MIN 8192u
 #define XX_PREFETCH_CHUNKS 16u
-ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
+// (out of line: inlined, its schedule depended on the kernel around it -- in one of the three kernels that use it the
+// chain's shared-memory loads were issued one at a time, right before their use, and the input ran 25 % slower)
+ZG_DEV_NOINLINE u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 	u32 lane = zg_lane();
 	u64 acc = lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;  // seed 0
 	u64 chunks = n >> 10;
