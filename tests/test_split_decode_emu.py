@@ -178,6 +178,30 @@ def test_short_blocks_are_not_mistaken_for_full_ones(emu):
     assert (n_frames, n_items, n_redo) == (3, 2 + 3 + 3, 0)  # blocks of any size are staged; nothing is decoded twice
 
 
+def test_checksums_hashed_chunk_by_chunk(emu):
+    """With several chunks per launch the Content_Checksum of a staged frame is absorbed piece by piece behind the chunks
+    (k_zds_xxh64_partial) and finished by the check: good frames pass, a wrong checksum field and a flipped content byte
+    that still decodes are reported as checksum_wrong, whatever the chunk size."""
+    files = [text(400_000, 51), text(300_000, 52) + rand(140_000, 53), text(9_000, 54), text(262_144, 55)]
+    frames = _own_frames(emu, files)
+    bad_ck = bytearray(frames[0])
+    bad_ck[-1] ^= 0x80
+    ref = [ref_path.ref_compress(f, level=1) for f in files]
+    # a stored (Raw) block's payload can be altered without breaking the frame: find one in the random part
+    batch = [frames[0], bytes(bad_ck), frames[1], frames[2], frames[3]] + ref
+    sizes = [len(files[0]), len(files[0]), len(files[1]), len(files[2]), len(files[3])] + [len(f) for f in files]
+    digs = [_b3(files[0]), _b3(files[0]), _b3(files[1]), _b3(files[2]), _b3(files[3])] + [_b3(f) for f in files]
+    try:
+        for chunk in (0, 1, 2, 5):
+            emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(chunk))
+            outs, ok, status, rc = unpack_batch(emu, batch, sizes, digs)
+            assert status == [0, 22, 0, 0, 0, 0, 0, 0, 0], (chunk, status)
+            assert ok == [1, 0, 1, 1, 1, 1, 1, 1, 1]
+            assert outs[0] == files[0] and outs[2] == files[1] and outs[5:] == files
+    finally:
+        emu.dll.zg_internal_set_decode_chunk_blocks(C.c_uint32(0))
+
+
 def test_corruption_inside_split_frames(emu):
     files = [text(400_000, 41), text(300_000, 42), text(290_000, 43), text(10_000, 44)]
     frames = _own_frames(emu, files)

@@ -32,3 +32,7 @@ def test_corruption_inside_split_frames(gpu):
 
 def test_chain_executor_window_edges_and_both_modes(gpu):
     cases.test_chain_executor_window_edges_and_both_modes(gpu)
+
+
+def test_checksums_hashed_chunk_by_chunk(gpu):
+    cases.test_checksums_hashed_chunk_by_chunk(gpu)

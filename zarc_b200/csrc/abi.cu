@@ -168,8 +168,8 @@ static size_t unpack_core(zg_dctx* d, const u8* archive, u64 archive_len, u64 n,
 		out_off = d->packed_off.as<u64>();
 	}
 	ZG_TRY(zg_zstd_decode_run(s, d->zd, archive, archive_len, off, len, ulen, out_off, n, out, out_cap, st, d->produced.as<u64>(),
-	                          d->cksums.as<u32>()));
-	ZG_TRY(zg_unpack_finalize_run(s, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum));
+	                          d->cksums.as<u32>(), d->verify_checksum));
+	ZG_TRY(zg_unpack_finalize_run(s, out, out_off, ulen, d->produced.as<u64>(), d->cksums.as<u32>(), st, n, d->verify_checksum, &d->zd));
 	if (digests && ok) {
 		ZG_ALLOC(d->got_digests.reserve(n * 32));
 		ZG_ALLOC(d->vspan.reserve(n * 16));

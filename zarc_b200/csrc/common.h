@@ -95,12 +95,26 @@ struct ZgZdStaged {  // the staged pipeline for multi-block frames (zstd_decode_
 	ZgBuf tail, f_out, f_rep, f_status, done_upto, f_chain;      // per frame: running state across chunks
 	ZgBuf item_of, chain_list;                                   // per block: its item in the chunk; frames for the chain executor
 	ZgBuf jbase, cursor, queue, items, seq_cnt, lit_cnt, seq_off, lit_off, seq_stage, lit_stage, tabs;  // per chunk
+	// Content_Checksum of the staged frames, hashed chunk by chunk on a side stream while the next chunk decodes:
+	// per frame the KiB chunks hashed so far and the four accumulators; the watermark snapshot of the chunk being hashed
+	ZgBuf xx_done, xx_acc, xx_wm;
+	u64 xx_n = 0;  // frames the state arrays of the last run cover (0: none)
+	cudaStream_t xx_stream = nullptr;
+	cudaEvent_t xx_fork = nullptr, xx_join = nullptr;
+	bool xx_init = false;
 	ZgHostBuf hh;
 	void release() {
 		for (ZgBuf* b : {&nblk, &first, &multi, &single, &tot, &hist, &blk, &res, &out_pos, &rep_in, &dep, &done, &tail, &f_out, &f_rep, &f_status,
-		                 &done_upto, &f_chain, &item_of, &chain_list, &jbase, &cursor, &queue, &items, &seq_cnt, &lit_cnt, &seq_off, &lit_off, &seq_stage, &lit_stage, &tabs})
+		                 &done_upto, &f_chain, &item_of, &chain_list, &jbase, &cursor, &queue, &items, &seq_cnt, &lit_cnt, &seq_off, &lit_off, &seq_stage, &lit_stage, &tabs, &xx_done, &xx_acc, &xx_wm})
 			b->release();
 		hh.release();
+		if (xx_stream) cudaStreamDestroy(xx_stream);
+		if (xx_fork) cudaEventDestroy(xx_fork);
+		if (xx_join) cudaEventDestroy(xx_join);
+		xx_stream = nullptr;
+		xx_fork = xx_join = nullptr;
+		xx_init = false;
+		xx_n = 0;
 	}
 };
 struct ZgZdWork {
@@ -121,11 +135,11 @@ struct ZgZdWork {
 };
 size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
                           const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,
-                          u32* cksums);
+                          u32* cksums, int verify_checksums = 0);
 
 // ---- glue.cu ----
 size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off, const u64* ulen, const u64* produced,
-                              const u32* cksums, u32* status, u64 n, int verify);
+                              const u32* cksums, u32* status, u64 n, int verify, const ZgZdWork* zw = nullptr);
 size_t zg_verify_spans_run(cudaStream_t s, const u32* status, const u64* out_off, const u64* ulen, u64 out_cap, u64 n, u64* voff, u64* vlen);
 size_t zg_digest_compare_run(cudaStream_t s, const u8* got, const u8* want, const u32* status, u8* ok, u64 n);
 size_t zg_first_error_run(cudaStream_t s, const u32* status, u64 n, u64* first);

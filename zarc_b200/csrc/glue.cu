@@ -22,12 +22,17 @@ k_unpack_finalize(const u8* __restrict__ out, const u64* __restrict__ out_off, c
 // k_unpack_finalize, which has already settled the size check
 __global__ void __launch_bounds__(128)
 k_unpack_checksum_warp(const u8* __restrict__ out, const u64* __restrict__ out_off, const u64* __restrict__ ulen,
-                       const u32* __restrict__ cksums, u32* __restrict__ status, u64 n) {
+                       const u32* __restrict__ cksums, u32* __restrict__ status, u64 n, const u64* __restrict__ xx_done,
+                       const u64* __restrict__ xx_acc) {
 	__shared__ u64 sb[4][128];
 	u64 k = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
 	if (k >= n) return;
 	if (ulen[k] < XX_WARP_MIN || status[k] != ZS_OK || !cksums[2 * k + 1]) return;
-	u64 h = xx_hash_warp(out + out_off[k], ulen[k], sb[threadIdx.x >> 5]);
+	// a staged frame may have been hashed in part already, while its later blocks were being decoded
+	u64 c0 = xx_done ? xx_done[k] : 0;
+	u64 acc = xx_warp_acc0();
+	if (c0 && (threadIdx.x & 31) < 4) acc = xx_acc[4 * k + (threadIdx.x & 31)];
+	u64 h = xx_hash_warp_from(out + out_off[k], ulen[k], c0, acc, sb[threadIdx.x >> 5]);
 	if ((threadIdx.x & 31) == 0 && (u32)h != cksums[2 * k]) status[k] = ZS_E_CHECKSUM;
 }
 
@@ -63,12 +68,14 @@ __global__ void __launch_bounds__(128) k_first_error(const u32* __restrict__ sta
 }
 
 size_t zg_unpack_finalize_run(cudaStream_t s, const u8* out, const u64* out_off, const u64* ulen, const u64* produced,
-                              const u32* cksums, u32* status, u64 n, int verify) {
+                              const u32* cksums, u32* status, u64 n, int verify, const ZgZdWork* zw) {
 	if (!n) return 0;
 	ZG_LAUNCH(k_unpack_finalize, (u32)((n + 127) / 128), 128, 0, s, out, out_off, ulen, produced, cksums, status, n, verify);
 	ZG_COUNT_LAUNCH();
 	if (verify) {
-		ZG_LAUNCH(k_unpack_checksum_warp, (u32)((n + 3) / 4), 128, 0, s, out, out_off, ulen, cksums, status, n);
+		const bool part = zw && zw->st.xx_n == n;  // the decode run just before left partial hashes for its staged frames
+		ZG_LAUNCH(k_unpack_checksum_warp, (u32)((n + 3) / 4), 128, 0, s, out, out_off, ulen, cksums, status, n,
+		          part ? zw->st.xx_done.as<u64>() : (const u64*)nullptr, part ? zw->st.xx_acc.as<u64>() : (const u64*)nullptr);
 		ZG_COUNT_LAUNCH();
 	}
 	return 0;

@@ -126,12 +126,13 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 // side by side).  `sb`: 128 u64 of shared memory per warp.  All lanes call; all lanes get the hash.
 #define XX_WARP_MIN 8192u
 #define XX_PREFETCH_CHUNKS 16u
+// The accumulators over the whole KiB chunks [c0, c1) of the input at p, continuing from `acc` (lane k < 4 carries
+// accumulator k in and out; the other lanes' value is ignored).  Resumable: a big input can be hashed piece by piece as
+// it becomes available (the staged decoder does).
 // (out of line: inlined, its schedule depended on the kernel around it -- in one of the three kernels that use it the
 // chain's shared-memory loads were issued one at a time, right before their use, and the input ran 25 % slower)
-ZG_DEV_NOINLINE u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
+ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb) {
 	u32 lane = zg_lane();
-	u64 acc = lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;  // seed 0
-	u64 chunks = n >> 10;
 	const u8* q = p + 32 * lane;
 	// The lane's 32 bytes of a chunk as aligned words; they are combined into four u64 (a funnel shift when the input is
 	// not word aligned) only AFTER the chains of the chunk before have run: combined at once, the shifts would wait for
@@ -141,22 +142,23 @@ ZG_DEV_NOINLINE u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 	u32 raw[9];
 	ZG_UNROLL
 	for (int k = 0; k < 9; k++) raw[k] = 0;
-	if (chunks) {
+	if (c0 < c1) {
+		const u32* w0 = wq + (c0 << 8);
 		ZG_UNROLL
-		for (int k = 0; k < 8; k++) raw[k] = wq[k];
-		if (sh) raw[8] = wq[8];
+		for (int k = 0; k < 8; k++) raw[k] = w0[k];
+		if (sh) raw[8] = w0[8];
 	}
-	for (u64 c = 0; c < chunks; c++) {
+	for (u64 c = c0; c < c1; c++) {
 		// a warp has one chunk in flight: without help it would stream at one DRAM latency per KiB (measured 1.3 GB/s on a
 		// 4 GiB input).  The lines 16 KiB ahead are asked into L2 now, so that the loads below find them there.
-		if (c + XX_PREFETCH_CHUNKS < chunks) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << 10));
+		if (c + XX_PREFETCH_CHUNKS < c1) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << 10));
 		ZG_UNROLL
 		for (int j = 0; j < 4; j++) {  // the products are off the chain: all 32 lanes make them
 			u64 r = ((u64)__funnelshift_r(raw[2 * j + 1], raw[2 * j + 2], sh) << 32) | __funnelshift_r(raw[2 * j], raw[2 * j + 1], sh);
 			sb[4 * lane + j] = r * XXP2;
 		}
 		__syncwarp();
-		if (c + 1 < chunks) {  // in flight while the chains run
+		if (c + 1 < c1) {  // in flight while the chains run
 			const u32* wn = wq + ((c + 1) << 8);
 			ZG_UNROLL
 			for (int k = 0; k < 8; k++) raw[k] = wn[k];
@@ -173,6 +175,17 @@ ZG_DEV_NOINLINE u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 		}
 		__syncwarp();
 	}
+	return acc;
+}
+ZG_DEV u64 xx_warp_acc0() {  // seed 0
+	u32 lane = zg_lane();
+	return lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;
+}
+// the hash of p[0..n) given the accumulators after its first c0 chunks (xx_warp_acc0() and 0 for the whole input)
+ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
+	u32 lane = zg_lane();
+	u64 chunks = n >> 10;
+	acc = xx_warp_chunks(p, c0, chunks, acc, sb);
 	XxState s;
 	s.v1 = __shfl_sync(ZG_FULL, acc, 0);
 	s.v2 = __shfl_sync(ZG_FULL, acc, 1);
@@ -190,3 +203,4 @@ ZG_DEV_NOINLINE u64 xx_hash_warp(const u8* p, u64 n, u64* sb) {
 	}
 	return __shfl_sync(ZG_FULL, h, 0);
 }
+ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) { return xx_hash_warp_from(p, n, 0, xx_warp_acc0(), sb); }

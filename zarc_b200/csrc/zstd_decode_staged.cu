@@ -30,6 +30,7 @@
 #include "common.h"
 #include "zstd_common.cuh"
 #include "zstd_decode.cuh"
+#include "xxh64.cuh"
 #include <vector>
 
 #define ZDS_NONE 0xffffffffu
@@ -960,6 +961,28 @@ k_zds_chain(ZdsJob J, const u32* __restrict__ chain_list, u32 nchain, const u64*
 	}
 }
 
+// The Content_Checksum of the staged frames, piece by piece: after a chunk of blocks has been executed, the whole KiB
+// chunks of every frame's output up to the watermark `wm` (a snapshot of f_out taken behind that chunk's execution) are
+// absorbed into the frame's accumulators.  Runs on a side stream while the next chunk of blocks is decoded: XXH64 is a
+// serial chain per frame (2 GB/s), so for a few huge frames it is as long as everything else together.
+__global__ void __launch_bounds__(128)
+k_zds_xxh64_partial(const u8* __restrict__ archive, const u64* __restrict__ off, const u8* __restrict__ out, const u64* __restrict__ out_off,
+                    const u32* __restrict__ multi, u64 nmulti, const u64* __restrict__ wm, u64* __restrict__ xx_done, u64* __restrict__ xx_acc) {
+	__shared__ u64 sb[4][128];
+	u64 m = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (m >= nmulti) return;
+	u32 lane = threadIdx.x & 31;
+	u32 k = multi[m];
+	if (!((archive[off[k] + 4] >> 2) & 1)) return;  // no Content_Checksum in this frame
+	u64 c0 = xx_done[k], c1 = wm[k] >> 10;
+	if (c1 <= c0) return;
+	u64 acc = xx_warp_acc0();
+	if (c0 && lane < 4) acc = xx_acc[4 * (u64)k + lane];
+	acc = xx_warp_chunks(out + out_off[k], c0, c1, acc, sb[threadIdx.x >> 5]);
+	if (lane < 4) xx_acc[4 * (u64)k + lane] = acc;
+	if (lane == 0) xx_done[k] = c1;
+}
+
 // frame results, as the serial decoder reports them
 __global__ void __launch_bounds__(128)
 k_zds_finish(const u8* __restrict__ archive, const u64* __restrict__ off, const u64* __restrict__ len, const u64* __restrict__ ulen,
@@ -1016,12 +1039,13 @@ size_t zd_fused_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archi
 
 size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archive_len, const u64* off, const u64* len,
                           const u64* ulen, const u64* out_off, u64 n, u8* out, u64 out_cap, u32* status, u64* produced,
-                          u32* cksums) {
+                          u32* cksums, int verify_checksums) {
 	if (n == 0) return 0;
 	if (n >= 0xffffffffull) return ZG_ERR(ZG_error_GENERIC);
 	for (int i = 0; i < 8; i++) g_zd_stats[i] = 0;
 	g_zd_stats[0] = g_zd_stats[1] = n;
 	ZgZdStaged& S = w.st;
+	S.xx_n = 0;
 	if (S.nblk.reserve(n * 4) || S.first.reserve(n * 8) || S.multi.reserve(n * 4) || S.single.reserve(n * 4) || S.tot.reserve(64) ||
 	    S.hist.reserve(((size_t)ZDS_HMAX + 2) * 4) || w.h.reserve(64))
 		return ZG_ERR(ZG_error_memory_allocation);
@@ -1135,6 +1159,23 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 	}
 	u64* totals = (u64*)S.tot.p + 4;  // [4] sequences, [5] literal bytes, [6] blocks that wait
 	cudaMemsetAsync(totals + 2, 0, 8, s);
+	// Content_Checksums of the staged frames: hashed chunk by chunk on a side stream (k_zds_xxh64_partial), worth it when
+	// the frames are few and long (several chunks); the check itself is zg_unpack_finalize_run's
+	bool xx_side = false;
+	if (verify_checksums && chunks.size() > 1) {
+		if (!S.xx_init) {
+			S.xx_init = true;
+			if (cudaStreamCreateWithFlags(&S.xx_stream, cudaStreamNonBlocking) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&S.xx_fork, cudaEventDisableTiming) != cudaSuccess ||
+			    cudaEventCreateWithFlags(&S.xx_join, cudaEventDisableTiming) != cudaSuccess)
+				S.xx_fork = S.xx_join = nullptr;
+		}
+		if (S.xx_fork && S.xx_join && !S.xx_done.reserve(n * 8) && !S.xx_acc.reserve(n * 32) && !S.xx_wm.reserve(n * 8)) {
+			xx_side = true;
+			cudaMemsetAsync(S.xx_done.p, 0, n * 8, s);
+		}
+	}
+	bool xx_pending = false;
 	for (auto& c : chunks) {
 		ZG_LAUNCH(k_zds_chunk_items, (u32)((nmulti + 3) / 4), 128, 0, s, S.multi.as<u32>(), nmulti, S.first.as<u64>(), S.nblk.as<u32>(),
 		          S.blk.as<ZdsBlk>(), c.J, c.w, S.jbase.as<u32>(), S.cursor.as<u32>(), S.items.as<u32>(), S.item_of.as<u32>(), S.seq_cnt.as<u64>(),
@@ -1178,9 +1219,26 @@ size_t zg_zstd_decode_run(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 ar
 			ZG_COUNT_LAUNCH();
 		}
 		zg_prof_end(ZG_K_DECODE, s);
+		if (xx_side) {
+			// what this chunk produced can be hashed while the next chunk decodes: the watermarks are snapshot behind the
+			// execution (f_out moves on with the next chunk's scan), once the side stream has finished with the last snapshot
+			cudaStream_t sx = S.xx_stream ? S.xx_stream : s;
+			if (xx_pending && cudaStreamWaitEvent(s, S.xx_join, 0) != cudaSuccess) return ZG_ERR(ZG_error_device);
+			cudaMemcpyAsync(S.xx_wm.p, S.f_out.p, n * 8, cudaMemcpyDeviceToDevice, s);
+			if (cudaEventRecord(S.xx_fork, s) != cudaSuccess || cudaStreamWaitEvent(sx, S.xx_fork, 0) != cudaSuccess) return ZG_ERR(ZG_error_device);
+			ZG_LAUNCH(k_zds_xxh64_partial, (u32)((nmulti + 3) / 4), 128, 0, sx, archive, off, out, out_off, S.multi.as<u32>(), nmulti,
+			          S.xx_wm.as<u64>(), S.xx_done.as<u64>(), S.xx_acc.as<u64>());
+			ZG_COUNT_LAUNCH();
+			if (cudaEventRecord(S.xx_join, sx) != cudaSuccess) return ZG_ERR(ZG_error_device);
+			xx_pending = true;
+		}
 		ZG_LAUNCH(k_zds_count_deps, (c.items + 255) / 256, 256, 0, s, S.blk.as<ZdsBlk>(), S.dep.as<u32>(), S.items.as<u32>(), c.items,
 		          (unsigned long long*)(totals + 2));
 		g_zg_launches += 4;
+	}
+	if (xx_pending) {
+		if (cudaStreamWaitEvent(s, S.xx_join, 0) != cudaSuccess) return ZG_ERR(ZG_error_device);
+		S.xx_n = n;
 	}
 	ZG_LAUNCH(k_zds_finish, gm, 128, 0, s, archive, off, len, ulen, S.multi.as<u32>(), nmulti, S.tail.as<u64>(), S.f_out.as<u64>(),
 	          S.f_status.as<u32>(), status, produced, cksums);
