@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128)
 k_unpack_checksum_warp(const u8* __restrict__ out, const u64* __restrict__ out_off, const u64* __restrict__ ulen,
                        const u32* __restrict__ cksums, u32* __restrict__ status, u64 n, const u64* __restrict__ xx_done,
                        const u64* __restrict__ xx_acc) {
-	__shared__ u64 sb[4][128];
+	__shared__ u64 sb[4][XX_SB_WORDS];
 	u64 k = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
 	if (k >= n) return;
 	if (ulen[k] < XX_WARP_MIN || status[k] != ZS_OK || !cksums[2 * k + 1]) return;

@@ -214,7 +214,7 @@ k_xxh64_list(const u8* __restrict__ blob, const u64* __restrict__ off, const u64
 __global__ void __launch_bounds__(128)
 k_xxh64_list_warp(const u8* __restrict__ blob, const u64* __restrict__ off, const u64* __restrict__ len, const u32* __restrict__ ulist,
                   u64 nuniq, u64* __restrict__ out) {
-	__shared__ u64 sb[4][128];
+	__shared__ u64 sb[4][XX_SB_WORDS];
 	u64 u = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
 	if (u >= nuniq) return;
 	u32 f = ulist[u];

@@ -12,7 +12,7 @@ k_xxh64(const u8* __restrict__ blob, const u64* __restrict__ off, const u64* __r
 // one warp per input of XX_WARP_MIN bytes and more (the others' warps leave at once)
 __global__ void __launch_bounds__(128)
 k_xxh64_warp(const u8* __restrict__ blob, const u64* __restrict__ off, const u64* __restrict__ len, u64 n, u64* __restrict__ out) {
-	__shared__ u64 sb[4][128];
+	__shared__ u64 sb[4][XX_SB_WORDS];
 	u64 i = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
 	if (i >= n || len[i] < XX_WARP_MIN) return;
 	u64 h = xx_hash_warp(blob + off[i], len[i], sb[threadIdx.x >> 5]);

@@ -120,13 +120,18 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 
 // Inputs of XX_WARP_MIN bytes and more are hashed by a whole warp.  The recurrence itself cannot be
 // split (each accumulator is a serial multiply-rotate chain over the stripes), but a single thread
-// also pays a memory round trip per 32-byte stripe; here the 32 lanes fetch 1 KiB (32 stripes) at a
+// also pays a memory round trip per 32-byte stripe; here the 32 lanes fetch a chunk (2 KiB: 64 stripes) at a
 // time, coalesced and one chunk ahead, into shared memory, and lanes 0..3 run one accumulator each
 // from there: the chain's arithmetic latency is all that is left (2 GB/s per input; many inputs run
-// side by side).  `sb`: 128 u64 of shared memory per warp.  All lanes call; all lanes get the hash.
+// side by side).  `sb`: XX_SB_WORDS u64 of shared memory per warp.  All lanes call; all lanes get the hash.
 #define XX_WARP_MIN 8192u
 #define XX_PREFETCH_CHUNKS 16u
-// The accumulators over the whole KiB chunks [c0, c1) of the input at p, continuing from `acc` (lane k < 4 carries
+// a warp's unit of work: 2 KiB (64 stripes per accumulator chain between two warp-wide hand-offs; with 1 KiB the
+// hand-off -- products, stores, barrier, the first loads of the chain -- was 22 % of a chunk's time)
+#define XX_CHUNK_KIB 2
+#define XX_CHUNK_SHIFT 11
+#define XX_SB_WORDS (128 * XX_CHUNK_KIB)   // u64 of shared memory per warp
+// The accumulators over the whole chunks (of 2^XX_CHUNK_SHIFT bytes) [c0, c1) of the input at p, continuing from `acc` (lane k < 4 carries
 // accumulator k in and out; the other lanes' value is ignored).  Resumable: a big input can be hashed piece by piece as
 // it becomes available (the staged decoder does).
 // (out of line: inlined, its schedule depended on the kernel around it -- in one of the three kernels that use it the
@@ -134,42 +139,58 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb) {
 	u32 lane = zg_lane();
 	const u8* q = p + 32 * lane;
-	// The lane's 32 bytes of a chunk as aligned words; they are combined into four u64 (a funnel shift when the input is
-	// not word aligned) only AFTER the chains of the chunk before have run: combined at once, the shifts would wait for
-	// the loads in front of the chains, and every chunk would cost a memory round trip on top of its 32 serial steps.
+	// The lane's stripes of a chunk (stripe `lane` and, 1 KiB on, stripe `lane + 32`) as aligned words; they are combined
+	// into u64 (a funnel shift when the input is not word aligned) only AFTER the chains of the chunk before have run:
+	// combined at once, the shifts would wait for the loads in front of the chains, and every chunk would cost a memory
+	// round trip on top of its serial steps.
 	const u32* wq = (const u32*)((uintptr_t)q & ~(uintptr_t)3);
 	const u32 sh = (u32)((uintptr_t)q & 3) * 8;
-	u32 raw[9];
+	u32 raw[XX_CHUNK_KIB][9];
 	ZG_UNROLL
-	for (int k = 0; k < 9; k++) raw[k] = 0;
-	if (c0 < c1) {
-		const u32* w0 = wq + (c0 << 8);
+	for (int h = 0; h < XX_CHUNK_KIB; h++) {
 		ZG_UNROLL
-		for (int k = 0; k < 8; k++) raw[k] = w0[k];
-		if (sh) raw[8] = w0[8];
+		for (int k = 0; k < 9; k++) raw[h][k] = 0;
+	}
+	if (c0 < c1) {
+		ZG_UNROLL
+		for (int h = 0; h < XX_CHUNK_KIB; h++) {
+			const u32* w0 = wq + (c0 << (XX_CHUNK_SHIFT - 2)) + 256 * h;
+			ZG_UNROLL
+			for (int k = 0; k < 8; k++) raw[h][k] = w0[k];
+			if (sh) raw[h][8] = w0[8];
+		}
 	}
 	for (u64 c = c0; c < c1; c++) {
-		// a warp has one chunk in flight: without help it would stream at one DRAM latency per KiB (measured 1.3 GB/s on a
-		// 4 GiB input).  The lines 16 KiB ahead are asked into L2 now, so that the loads below find them there.
-		if (c + XX_PREFETCH_CHUNKS < c1) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << 10));
+		// a warp has one chunk in flight: without help it would stream at one DRAM latency per chunk (measured 1.3 GB/s on
+		// a 4 GiB input).  The lines 16 chunks ahead are asked into L2 now, so that the loads below find them there.
+		if (c + XX_PREFETCH_CHUNKS < c1) {
+			ZG_UNROLL
+			for (int h = 0; h < XX_CHUNK_KIB; h++) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << XX_CHUNK_SHIFT) + 1024 * h);
+		}
 		ZG_UNROLL
-		for (int j = 0; j < 4; j++) {  // the products are off the chain: all 32 lanes make them
-			u64 r = ((u64)__funnelshift_r(raw[2 * j + 1], raw[2 * j + 2], sh) << 32) | __funnelshift_r(raw[2 * j], raw[2 * j + 1], sh);
-			sb[4 * lane + j] = r * XXP2;
+		for (int h = 0; h < XX_CHUNK_KIB; h++) {
+			ZG_UNROLL
+			for (int j = 0; j < 4; j++) {  // the products are off the chain: all 32 lanes make them
+				u64 r = ((u64)__funnelshift_r(raw[h][2 * j + 1], raw[h][2 * j + 2], sh) << 32) | __funnelshift_r(raw[h][2 * j], raw[h][2 * j + 1], sh);
+				sb[128 * h + 4 * lane + j] = r * XXP2;
+			}
 		}
 		__syncwarp();
 		if (c + 1 < c1) {  // in flight while the chains run
-			const u32* wn = wq + ((c + 1) << 8);
 			ZG_UNROLL
-			for (int k = 0; k < 8; k++) raw[k] = wn[k];
-			if (sh) raw[8] = wn[8];
+			for (int h = 0; h < XX_CHUNK_KIB; h++) {
+				const u32* wn = wq + ((c + 1) << (XX_CHUNK_SHIFT - 2)) + 256 * h;
+				ZG_UNROLL
+				for (int k = 0; k < 8; k++) raw[h][k] = wn[k];
+				if (sh) raw[h][8] = wn[8];
+			}
 		}
 		if (lane < 4) {
-			// b = acc + x0, then 32 steps each absorbing the next stripe's x (the last one absorbs 0: b becomes acc)
+			// b = acc + x0, then one step per stripe, each absorbing the next stripe's x (the last absorbs 0: b becomes acc)
 			XxChain ch;
 			xx_chain_start(ch, acc, sb[lane]);
 			ZG_UNROLL
-			for (u32 i = 1; i < 32; i++) xx_chain_step(ch, sb[4 * i + lane]);
+			for (u32 i = 1; i < 32 * XX_CHUNK_KIB; i++) xx_chain_step(ch, sb[4 * i + lane]);
 			xx_chain_step(ch, 0);
 			acc = xx_chain_value(ch);
 		}
@@ -184,7 +205,7 @@ ZG_DEV u64 xx_warp_acc0() {  // seed 0
 // the hash of p[0..n) given the accumulators after its first c0 chunks (xx_warp_acc0() and 0 for the whole input)
 ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
 	u32 lane = zg_lane();
-	u64 chunks = n >> 10;
+	u64 chunks = n >> XX_CHUNK_SHIFT;
 	acc = xx_warp_chunks(p, c0, chunks, acc, sb);
 	XxState s;
 	s.v1 = __shfl_sync(ZG_FULL, acc, 0);
@@ -193,8 +214,8 @@ ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
 	s.v4 = __shfl_sync(ZG_FULL, acc, 3);
 	u64 h = 0;
 	if (lane == 0) {
-		const u8* t = p + (chunks << 10);
-		u64 stripes = (n >> 5) - (chunks << 5);  // < 32 left
+		const u8* t = p + (chunks << XX_CHUNK_SHIFT);
+		u64 stripes = (n >> 5) - (chunks << (XX_CHUNK_SHIFT - 5));  // fewer than a chunk's worth left
 		for (u64 i = 0; i < stripes; i++) {
 			const u8* b = t + 32 * i;
 			xx_stripe(s, zg_ld64(b), zg_ld64(b + 8), zg_ld64(b + 16), zg_ld64(b + 24));

@@ -968,13 +968,13 @@ k_zds_chain(ZdsJob J, const u32* __restrict__ chain_list, u32 nchain, const u64*
 __global__ void __launch_bounds__(128)
 k_zds_xxh64_partial(const u8* __restrict__ archive, const u64* __restrict__ off, const u8* __restrict__ out, const u64* __restrict__ out_off,
                     const u32* __restrict__ multi, u64 nmulti, const u64* __restrict__ wm, u64* __restrict__ xx_done, u64* __restrict__ xx_acc) {
-	__shared__ u64 sb[4][128];
+	__shared__ u64 sb[4][XX_SB_WORDS];
 	u64 m = (u64)blockIdx.x * 4 + (threadIdx.x >> 5);
 	if (m >= nmulti) return;
 	u32 lane = threadIdx.x & 31;
 	u32 k = multi[m];
 	if (!((archive[off[k] + 4] >> 2) & 1)) return;  // no Content_Checksum in this frame
-	u64 c0 = xx_done[k], c1 = wm[k] >> 10;
+	u64 c0 = xx_done[k], c1 = wm[k] >> XX_CHUNK_SHIFT;
 	if (c1 <= c0) return;
 	u64 acc = xx_warp_acc0();
 	if (c0 && lane < 4) acc = xx_acc[4 * (u64)k + lane];
