@@ -128,7 +128,10 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 #define XX_PREFETCH_CHUNKS 16u
 // a warp's unit of work: 2 KiB (64 stripes per accumulator chain between two warp-wide hand-offs; with 1 KiB the
 // hand-off -- products, stores, barrier, the first loads of the chain -- was 22 % of a chunk's time)
-#define XX_CHUNK_KIB 2
+// (inputs below XX_BIG_MIN keep 1 KiB: a 2 KiB unit leaves up to 63 stripes to the serial tail of lane 0, and the
+// 8-64 KiB files of a source tree hash 10 % slower with it)
+#define XX_BIG_MIN (1u << 20)
+#define XX_CHUNK_KIB 2                     // unit of inputs of XX_BIG_MIN bytes and more, and of resumed (staged) hashes
 #define XX_CHUNK_SHIFT 11
 #define XX_SB_WORDS (128 * XX_CHUNK_KIB)   // u64 of shared memory per warp
 // The accumulators over the whole chunks (of 2^XX_CHUNK_SHIFT bytes) [c0, c1) of the input at p, continuing from `acc` (lane k < 4 carries
@@ -136,7 +139,9 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 // it becomes available (the staged decoder does).
 // (out of line: inlined, its schedule depended on the kernel around it -- in one of the three kernels that use it the
 // chain's shared-memory loads were issued one at a time, right before their use, and the input ran 25 % slower)
-ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb) {
+template <int KIB>
+ZG_DEV_NOINLINE u64 xx_warp_chunks_t(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb) {
+	constexpr int SHIFT = 9 + KIB;  // 1 KiB: 10, 2 KiB: 11
 	u32 lane = zg_lane();
 	const u8* q = p + 32 * lane;
 	// The lane's stripes of a chunk (stripe `lane` and, 1 KiB on, stripe `lane + 32`) as aligned words; they are combined
@@ -145,16 +150,16 @@ ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb
 	// round trip on top of its serial steps.
 	const u32* wq = (const u32*)((uintptr_t)q & ~(uintptr_t)3);
 	const u32 sh = (u32)((uintptr_t)q & 3) * 8;
-	u32 raw[XX_CHUNK_KIB][9];
+	u32 raw[KIB][9];
 	ZG_UNROLL
-	for (int h = 0; h < XX_CHUNK_KIB; h++) {
+	for (int h = 0; h < KIB; h++) {
 		ZG_UNROLL
 		for (int k = 0; k < 9; k++) raw[h][k] = 0;
 	}
 	if (c0 < c1) {
 		ZG_UNROLL
-		for (int h = 0; h < XX_CHUNK_KIB; h++) {
-			const u32* w0 = wq + (c0 << (XX_CHUNK_SHIFT - 2)) + 256 * h;
+		for (int h = 0; h < KIB; h++) {
+			const u32* w0 = wq + (c0 << (SHIFT - 2)) + 256 * h;
 			ZG_UNROLL
 			for (int k = 0; k < 8; k++) raw[h][k] = w0[k];
 			if (sh) raw[h][8] = w0[8];
@@ -165,10 +170,10 @@ ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb
 		// a 4 GiB input).  The lines 16 chunks ahead are asked into L2 now, so that the loads below find them there.
 		if (c + XX_PREFETCH_CHUNKS < c1) {
 			ZG_UNROLL
-			for (int h = 0; h < XX_CHUNK_KIB; h++) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << XX_CHUNK_SHIFT) + 1024 * h);
+			for (int h = 0; h < KIB; h++) zg_prefetch_l2(q + ((c + XX_PREFETCH_CHUNKS) << SHIFT) + 1024 * h);
 		}
 		ZG_UNROLL
-		for (int h = 0; h < XX_CHUNK_KIB; h++) {
+		for (int h = 0; h < KIB; h++) {
 			ZG_UNROLL
 			for (int j = 0; j < 4; j++) {  // the products are off the chain: all 32 lanes make them
 				u64 r = ((u64)__funnelshift_r(raw[h][2 * j + 1], raw[h][2 * j + 2], sh) << 32) | __funnelshift_r(raw[h][2 * j], raw[h][2 * j + 1], sh);
@@ -178,8 +183,8 @@ ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb
 		__syncwarp();
 		if (c + 1 < c1) {  // in flight while the chains run
 			ZG_UNROLL
-			for (int h = 0; h < XX_CHUNK_KIB; h++) {
-				const u32* wn = wq + ((c + 1) << (XX_CHUNK_SHIFT - 2)) + 256 * h;
+			for (int h = 0; h < KIB; h++) {
+				const u32* wn = wq + ((c + 1) << (SHIFT - 2)) + 256 * h;
 				ZG_UNROLL
 				for (int k = 0; k < 8; k++) raw[h][k] = wn[k];
 				if (sh) raw[h][8] = wn[8];
@@ -190,7 +195,7 @@ ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb
 			XxChain ch;
 			xx_chain_start(ch, acc, sb[lane]);
 			ZG_UNROLL
-			for (u32 i = 1; i < 32 * XX_CHUNK_KIB; i++) xx_chain_step(ch, sb[4 * i + lane]);
+			for (u32 i = 1; i < 32 * KIB; i++) xx_chain_step(ch, sb[4 * i + lane]);
 			xx_chain_step(ch, 0);
 			acc = xx_chain_value(ch);
 		}
@@ -198,15 +203,18 @@ ZG_DEV_NOINLINE u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb
 	}
 	return acc;
 }
+ZG_DEV u64 xx_warp_chunks(const u8* p, u64 c0, u64 c1, u64 acc, u64* sb) { return xx_warp_chunks_t<XX_CHUNK_KIB>(p, c0, c1, acc, sb); }
 ZG_DEV u64 xx_warp_acc0() {  // seed 0
 	u32 lane = zg_lane();
 	return lane == 0 ? XXP1 + XXP2 : lane == 1 ? XXP2 : lane == 2 ? 0ull : 0ull - XXP1;
 }
-// the hash of p[0..n) given the accumulators after its first c0 chunks (xx_warp_acc0() and 0 for the whole input)
-ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
+// the hash of p[0..n) given the accumulators after its first c0 chunks of KIB KiB (xx_warp_acc0() and 0 for the whole input)
+template <int KIB>
+ZG_DEV u64 xx_hash_warp_from_t(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
+	constexpr int SHIFT = 9 + KIB;
 	u32 lane = zg_lane();
-	u64 chunks = n >> XX_CHUNK_SHIFT;
-	acc = xx_warp_chunks(p, c0, chunks, acc, sb);
+	u64 chunks = n >> SHIFT;
+	acc = xx_warp_chunks_t<KIB>(p, c0, chunks, acc, sb);
 	XxState s;
 	s.v1 = __shfl_sync(ZG_FULL, acc, 0);
 	s.v2 = __shfl_sync(ZG_FULL, acc, 1);
@@ -214,8 +222,8 @@ ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
 	s.v4 = __shfl_sync(ZG_FULL, acc, 3);
 	u64 h = 0;
 	if (lane == 0) {
-		const u8* t = p + (chunks << XX_CHUNK_SHIFT);
-		u64 stripes = (n >> 5) - (chunks << (XX_CHUNK_SHIFT - 5));  // fewer than a chunk's worth left
+		const u8* t = p + (chunks << SHIFT);
+		u64 stripes = (n >> 5) - (chunks << (SHIFT - 5));  // fewer than a chunk's worth left
 		for (u64 i = 0; i < stripes; i++) {
 			const u8* b = t + 32 * i;
 			xx_stripe(s, zg_ld64(b), zg_ld64(b + 8), zg_ld64(b + 16), zg_ld64(b + 24));
@@ -223,5 +231,10 @@ ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
 		h = xx_finish(s, t + 32 * stripes, n, 0);
 	}
 	return __shfl_sync(ZG_FULL, h, 0);
+}
+// resumed from a staged frame's partial hash (units of XX_CHUNK_KIB), or from the start
+ZG_DEV u64 xx_hash_warp_from(const u8* p, u64 n, u64 c0, u64 acc, u64* sb) {
+	if (c0 || n >= XX_BIG_MIN) return xx_hash_warp_from_t<XX_CHUNK_KIB>(p, n, c0, acc, sb);
+	return xx_hash_warp_from_t<1>(p, n, 0, acc, sb);
 }
 ZG_DEV u64 xx_hash_warp(const u8* p, u64 n, u64* sb) { return xx_hash_warp_from(p, n, 0, xx_warp_acc0(), sb); }
