@@ -581,28 +581,57 @@ ZG_DEV_NOINLINE u32 ze_huf_write_tree(ZeWarp* W, u32 maxsym) {
 				ze_fse_build_ctable_warp(ct, e.norm, maxw, e.tsym, e.cumul);
 				__syncwarp();
 				if (lane == 0) {
-					ZeBitW bw;
-					ze_bw_init(bw, e.wdesc + 1 + nc, e.wdesc + 128);
+					// The two-state FSE stream of the weights, serial by nature: kept as short as it can be -- bits gathered
+					// in a 64-bit register and handed to shared memory 32 at a time (no per-byte stores, no bounds checks:
+					// <= 255 symbols of <= 6 bits fit the 384-byte window); the warp copies the bytes out afterwards.
+					u32* win = e.window;
+					u64 acc = 0;
+					u32 nbits = 0, wi = 0;
+					auto put = [&](u32 v, u32 nb) {
+						acc |= (u64)(v & ((1u << nb) - 1u)) << nbits;
+						nbits += nb;
+						if (nbits >= 32) {
+							win[wi++] = (u32)acc;
+							acc >>= 32;
+							nbits -= 32;
+						}
+					};
+					auto enc = [&](u32& state, u32 sym) {
+						ZeSymTT r = ct.tt[sym];
+						u32 nb = (state + r.dnb) >> 16;
+						put(state, nb);
+						state = ct.st[(state >> nb) + r.dfs];
+					};
 					u32 ip = nw, s1, s2;
 					// libzstd FSE_compress_usingCTable order: the last two weights seed the two states
 					if (nw & 1) {
 						s1 = ze_fse_init_state(ct, e.hweight[--ip]);
 						s2 = ze_fse_init_state(ct, e.hweight[--ip]);
-						ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
+						enc(s1, e.hweight[--ip]);
 					} else {
 						s2 = ze_fse_init_state(ct, e.hweight[--ip]);
 						s1 = ze_fse_init_state(ct, e.hweight[--ip]);
 					}
 					ZG_UNROLL1
 					while (ip > 0) {
-						ze_fse_encode(bw, ct, s2, e.hweight[--ip]);
-						ze_fse_encode(bw, ct, s1, e.hweight[--ip]);
+						enc(s2, e.hweight[--ip]);
+						enc(s1, e.hweight[--ip]);
 					}
-					ze_fse_flush_state(bw, ct, s2);
-					ze_fse_flush_state(bw, ct, s1);
-					u8* endp = ze_bw_close(bw);
-					u32 csz = (u32)(endp - (e.wdesc + 1));
-					W->misc[2] = (!bw.ovf && csz < 128) ? 1 + csz : 0;
+					put(s2, log);
+					put(s1, log);
+					put(1, 1);  // the end marker
+					u32 sbytes = 4 * wi + ((nbits + 7) >> 3);
+					if (nbits) win[wi] = (u32)acc;
+					W->misc[2] = sbytes;
+				}
+				__syncwarp();
+				{
+					u32 sbytes = W->misc[2];
+					bool fits = nc + sbytes < 128;
+					if (fits)
+						for (u32 i = lane; i < sbytes; i += 32) e.wdesc[1 + nc + i] = (u8)(e.window[i >> 2] >> (8 * (i & 3)));
+					__syncwarp();
+					if (lane == 0) W->misc[2] = fits ? 1 + nc + sbytes : 0;
 				}
 				__syncwarp();
 				fse_size = W->misc[2];
