@@ -662,6 +662,8 @@ def main():
         lib.dll.zg_internal_set_decode_chain_mode(C.c_uint32(int(os.environ["ZG_CHAIN_MODE"])))
     if os.environ.get("ZG_SLICE_MB"):  # tuning aid: host-API slice size
         lib.dll.zg_internal_set_slice_bytes(C.c_uint64(int(os.environ["ZG_SLICE_MB"]) << 20))
+    if os.environ.get("ZG_UNPACK_WORKERS"):  # tuning aid: slices decoded at the same time by the host API
+        lib.dll.zg_internal_set_unpack_workers(C.c_int(int(os.environ["ZG_UNPACK_WORKERS"])))
     if os.environ.get("ZG_PACK_SLICE_MB"):  # tuning aid: host-API slice size, pack only
         lib.dll.zg_internal_set_pack_slice_bytes(C.c_uint64(int(os.environ["ZG_PACK_SLICE_MB"]) << 20))
 

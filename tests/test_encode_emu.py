@@ -184,6 +184,34 @@ def test_sliced_host_api_and_chunked_encoder_equal_one_shot(emu):
     assert all(x == results[0] for x in results[1:])
 
 
+@pytest.mark.parametrize("workers", [1, 2, 4])
+def test_sliced_unpack_workers_and_frame_errors(emu, workers):
+    """zg_unpack_batch decodes its slices with several contexts at once (host threads; the CPU test build runs them one
+    after the other): whatever the worker count, every intact file comes back, a damaged frame is named in its own
+    status entry, and the call's return code is the error of the FIRST damaged frame in batch order."""
+    import ctypes as C
+
+    files = [rand(3000 + 517 * i, 40 + i) + bytes(2000 + 10 * i) for i in range(40)]
+    frames = [bytes(compress2(emu, f)) for f in files]
+    digests = [ref_path.c_blake3(f) for f in files]
+    try:
+        emu.dll.zg_internal_set_slice_bytes(C.c_uint64(20_000))
+        emu.dll.zg_internal_set_unpack_workers(C.c_int(workers))
+        outs, ok, status, rc = unpack_batch(emu, frames, [len(f) for f in files], digests)
+        assert rc == 0 and outs == files and all(ok) and not any(status)
+        bad = list(frames)
+        bad[31] = bad[31][:4] + bytes([bad[31][4] | 0x08]) + bad[31][5:]  # reserved bit of the frame header descriptor
+        bad[7] = bad[7][:-4] + bytes(4)                                    # content checksum
+        outs, ok, status, rc = unpack_batch(emu, bad, [len(f) for f in files], digests)
+        assert emu.zg_get_error_code(rc) == 22  # checksum_wrong: frame 7 comes first
+        assert status[7] == 22 and status[31] == 14 and [i for i, v in enumerate(status) if v] == [7, 31]
+        assert all(o == f for i, (o, f) in enumerate(zip(outs, files)) if i not in (7, 31))
+        assert [i for i, v in enumerate(ok) if not v] == [7, 31]
+    finally:
+        emu.dll.zg_internal_set_slice_bytes(C.c_uint64(0))
+        emu.dll.zg_internal_set_unpack_workers(C.c_int(0))
+
+
 def _pack_with(emu, files, level=3, params=()):
     cctx = emu.zg_cctx_create()
     emu.check(emu.zg_cctx_init(cctx, 0))

@@ -42,6 +42,15 @@ def test_pack_batch_capacity_error(gpu):
     cases.test_pack_batch_capacity_error(gpu)
 
 
+def test_sliced_host_api_and_chunked_encoder_equal_one_shot(gpu):
+    cases.test_sliced_host_api_and_chunked_encoder_equal_one_shot(gpu)
+
+
+@pytest.mark.parametrize("workers", [1, 2, 4])
+def test_sliced_unpack_workers_and_frame_errors(gpu, workers):
+    cases.test_sliced_unpack_workers_and_frame_errors(gpu, workers)
+
+
 def _roundtrip_corpus(gpu, c, level, sample_every):
     import blake3
 

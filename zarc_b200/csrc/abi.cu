@@ -5,7 +5,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 #include <string.h>
@@ -109,6 +111,9 @@ static size_t host_frame_size(const uint8_t* p, size_t n, uint64_t* bound, bool*
 }
 
 // ---------------------------------------------------------------------------------------------
+#define ZG_UNPACK_WORKERS_MAX 4
+int g_zg_unpack_workers = 2;
+extern "C" void zg_internal_set_unpack_workers(int v) { g_zg_unpack_workers = v < 1 ? 2 : v > ZG_UNPACK_WORKERS_MAX ? ZG_UNPACK_WORKERS_MAX : v; }
 struct zg_dctx {
 	cudaStream_t stream = 0;
 	bool own_stream = false;
@@ -116,12 +121,15 @@ struct zg_dctx {
 	ZgZdWork zd;
 	ZgB3Work b3;
 	ZgBuf status, produced, cksums, got_digests, first, tiles, packed_off, vspan;
-	// host-API staging: two stages, so that the copies of one slice overlap the kernels of another
+	// host-API staging: two stages per worker, so that the copies of one slice overlap the kernels of another.  Slices
+	// are decoded by ZG_UNPACK_WORKERS_MAX contexts at once (this one and its helpers, a host thread each): the
+	// persistent decode kernel of one slice drains while the next slice's fills the SMs it leaves.
 	struct Stage {
 		ZgBuf d_archive, d_meta, d_out, d_digests, d_ok;
 		ZgHostBuf h_small;
 		cudaEvent_t in_done = nullptr, out_done = nullptr;
-	} hstage[2];
+	} hstage[2 * ZG_UNPACK_WORKERS_MAX];
+	zg_dctx* helper[ZG_UNPACK_WORKERS_MAX - 1] = {};
 	cudaStream_t s_in = nullptr, s_out = nullptr;
 	ZgBuf d_archive, d_out, d_meta;  // one-shot / streaming paths
 	ZgHostBuf h_first, h_small;
@@ -410,6 +418,10 @@ zg_dctx* zg_dctx_create(void) {
 }
 void zg_dctx_free(zg_dctx* d) {
 	if (!d) return;
+	for (zg_dctx*& h : d->helper) {
+		zg_dctx_free(h);
+		h = nullptr;
+	}
 	cudaStreamSynchronize(d->stream);
 	d->zd.release();
 	zg_b3work_free(d->b3);
@@ -523,9 +535,24 @@ static size_t unpack_batch_impl(zg_dctx* d, const uint8_t* archive, uint64_t arc
 			sl.assign(1, all);
 		}
 	}
+	// workers: contexts decoding slices at the same time (slice k belongs to worker k % nw and to stage k % nst)
+#ifdef ZG_EMU
+	size_t nw = 1;  // (the CPU test build runs kernels on the calling thread)
+#else
+	size_t nw = (size_t)g_zg_unpack_workers < sl.size() ? (size_t)g_zg_unpack_workers : sl.size();
+#endif
+	int dev = 0;
+	ZG_CUDA(cudaGetDevice(&dev));
+	for (size_t w = 1; w < nw; w++) {
+		if (!d->helper[w - 1] && !(d->helper[w - 1] = zg_dctx_create())) return ZG_ERR(ZG_error_memory_allocation);
+		d->helper[w - 1]->verify_checksum = d->verify_checksum;
+	}
+	const size_t nst = 2 * nw;
+	std::mutex up_mu;
 	auto upload = [&](size_t k) -> size_t {
+		std::lock_guard<std::mutex> lk(up_mu);
 		const Slice& q = sl[k];
-		auto& st = d->hstage[k & 1];
+		auto& st = d->hstage[k % nst];
 		u64 m = q.i1 - q.i0, span = q.hi - q.lo, ospan = q.ohi - q.olo;
 		ZG_ALLOC(st.d_archive.reserve(span + 16));
 		ZG_ALLOC(st.d_meta.reserve(m * 32));
@@ -540,7 +567,8 @@ static size_t unpack_batch_impl(zg_dctx* d, const uint8_t* archive, uint64_t arc
 			h_oo[i] = dense ? acc : out_off[q.i0 + i] - q.olo;
 			acc += ulen[q.i0 + i];
 		}
-		ZG_CUDA(cudaStreamWaitEvent(d->s_in, st.out_done, 0));  // the stage's previous results have left
+		// (the stage's input buffers are free: the slice that used them has been decoded.  Its RESULTS may still be on
+		// their way down -- that is the decoding stream's wait, not this upload's: both directions stay busy)
 		u64* dm = st.d_meta.as<u64>();
 		ZG_CUDA(cudaMemcpyAsync(st.d_archive.p, archive + q.lo, span, cudaMemcpyHostToDevice, d->s_in));
 		ZG_CUDA(cudaMemcpyAsync(dm, h_off, m * 8, cudaMemcpyHostToDevice, d->s_in));
@@ -557,51 +585,101 @@ static size_t unpack_batch_impl(zg_dctx* d, const uint8_t* archive, uint64_t arc
 	const bool trace = getenv("ZG_TRACE") != nullptr;
 	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	double t_begin = now_ms();
-	size_t r = upload(0), first_err = 0;
-	for (size_t k = 0; k < sl.size() && !zg_is_error(r); k++) {
-		const Slice& q = sl[k];
-		auto& st = d->hstage[k & 1];
-		u64 m = q.i1 - q.i0, span = q.hi - q.lo, ospan = q.ohi - q.olo;
-		if (k + 1 < sl.size()) {
-			r = upload(k + 1);
-			if (zg_is_error(r)) break;
+	std::atomic<bool> stop{false};
+	// one worker: its slices in order; a fatal error (device, memory) stops every worker, a frame's error is kept and
+	// the other frames are still delivered
+	struct Result {
+		size_t fatal = 0, first_err = 0;
+		u64 first_err_slice = ~0ull;
+	};
+	std::vector<Result> res(nw);
+	auto work = [&](size_t w) {
+		Result& R = res[w];
+		zg_dctx* c = w ? d->helper[w - 1] : d;
+		if (w && cudaSetDevice(dev) != cudaSuccess) {
+			R.fatal = ZG_ERR(ZG_error_device);
+			stop = true;
+			return;
 		}
-		u64* dm = st.d_meta.as<u64>();
-		u8* d_dig = (digests && ok) ? st.d_digests.as<u8>() : nullptr;
-		u8* d_okp = st.d_ok.as<u8>();
-		u32* d_status = (u32*)(d_okp + ((m + 3) & ~(u64)3));
-		if (cudaStreamWaitEvent(s, st.in_done, 0) != cudaSuccess) {
-			r = ZG_ERR(ZG_error_device);
-			break;
-		}
-		double t2 = now_ms();
-		size_t rk = unpack_core(d, st.d_archive.as<u8>(), span, m, dm, dm + m, dm + 2 * m, d_dig, st.d_out.as<u8>(), ospan, dm + 3 * m,
-		                        d_dig ? d_okp : nullptr, d_status);
-		if (trace) fprintf(stderr, "[zg unpack] slice %zu: frames %llu out %llu  core starts +%.2f ms, takes %.2f ms\n", k, (unsigned long long)m,
-		                   (unsigned long long)q.obytes, t2 - t_begin, now_ms() - t2);
-		if (zg_is_error(rk)) {
-			if (zg_get_error_code(rk) == ZG_error_device || zg_get_error_code(rk) == ZG_error_memory_allocation) {
-				r = rk;
+		for (size_t k = w; k < sl.size() && !stop; k += nw) {
+			const Slice& q = sl[k];
+			auto& st = d->hstage[k % nst];
+			u64 m = q.i1 - q.i0, span = q.hi - q.lo, ospan = q.ohi - q.olo;
+			u64* dm = st.d_meta.as<u64>();
+			u8* d_dig = (digests && ok) ? st.d_digests.as<u8>() : nullptr;
+			u8* d_okp = st.d_ok.as<u8>();
+			u32* d_status = (u32*)(d_okp + ((m + 3) & ~(u64)3));
+			// the slice's input has arrived, and the stage's previous results have left
+			if (cudaStreamWaitEvent(c->stream, st.in_done, 0) != cudaSuccess || cudaStreamWaitEvent(c->stream, st.out_done, 0) != cudaSuccess) {
+				R.fatal = ZG_ERR(ZG_error_device);
 				break;
 			}
-			if (!first_err) first_err = rk;  // a frame failed: its status says which; the other frames are still delivered
+			double t2 = now_ms();
+			size_t rk = unpack_core(c, st.d_archive.as<u8>(), span, m, dm, dm + m, dm + 2 * m, d_dig, st.d_out.as<u8>(), ospan, dm + 3 * m,
+			                        d_dig ? d_okp : nullptr, d_status);
+			if (trace) fprintf(stderr, "[zg unpack] slice %zu (worker %zu): frames %llu out %llu  core starts +%.2f ms, takes %.2f ms\n", k, w,
+			                   (unsigned long long)m, (unsigned long long)q.obytes, t2 - t_begin, now_ms() - t2);
+			if (zg_is_error(rk)) {
+				if (zg_get_error_code(rk) == ZG_error_device || zg_get_error_code(rk) == ZG_error_memory_allocation) {
+					R.fatal = rk;
+					break;
+				}
+				if (!R.first_err) R.first_err = rk, R.first_err_slice = k;
+			}
+			cudaError_t e = cudaSuccess;
+			{
+				std::lock_guard<std::mutex> lk(up_mu);  // (s_out is shared: one slice's results are enqueued as a unit)
+				if (!dense) {
+					std::vector<u8> tmp(ospan);
+					e = cudaMemcpyAsync(tmp.data(), st.d_out.p, ospan, cudaMemcpyDeviceToHost, c->stream);
+					if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+					if (e == cudaSuccess)
+						for (u64 i = q.i0; i < q.i1; i++) memcpy(out + out_off[i], tmp.data() + (out_off[i] - q.olo), ulen[i]);
+				} else if (q.obytes) {
+					e = cudaMemcpyAsync(out + q.obase, st.d_out.p, q.obytes, cudaMemcpyDeviceToHost, d->s_out);
+				}
+				if (d_dig && e == cudaSuccess) e = cudaMemcpyAsync(ok + q.i0, d_okp, m, cudaMemcpyDeviceToHost, d->s_out);
+				if (status && e == cudaSuccess) e = cudaMemcpyAsync(status + q.i0, d_status, m * 4, cudaMemcpyDeviceToHost, d->s_out);
+				if (e == cudaSuccess) e = cudaEventRecord(st.out_done, d->s_out);
+			}
+			if (e != cudaSuccess) {
+				R.fatal = ZG_ERR(ZG_error_device);
+				break;
+			}
+			if (k + nst < sl.size()) {  // the stage is free again once these results have left: its next slice may come up
+				size_t ru = upload(k + nst);
+				if (zg_is_error(ru)) {
+					R.fatal = ru;
+					break;
+				}
+			}
 		}
-		cudaError_t e = cudaSuccess;
-		if (!dense) {
-			std::vector<u8> tmp(ospan);
-			e = cudaMemcpyAsync(tmp.data(), st.d_out.p, ospan, cudaMemcpyDeviceToHost, s);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-			if (e == cudaSuccess)
-				for (u64 i = q.i0; i < q.i1; i++) memcpy(out + out_off[i], tmp.data() + (out_off[i] - q.olo), ulen[i]);
-		} else if (q.obytes) {
-			e = cudaMemcpyAsync(out + q.obase, st.d_out.p, q.obytes, cudaMemcpyDeviceToHost, d->s_out);
-		}
-		if (d_dig && e == cudaSuccess) e = cudaMemcpyAsync(ok + q.i0, d_okp, m, cudaMemcpyDeviceToHost, d->s_out);
-		if (status && e == cudaSuccess) e = cudaMemcpyAsync(status + q.i0, d_status, m * 4, cudaMemcpyDeviceToHost, d->s_out);
-		if (e == cudaSuccess) e = cudaEventRecord(st.out_done, d->s_out);
-		if (e != cudaSuccess) {
-			r = ZG_ERR(ZG_error_device);
-			break;
+		if (R.fatal) stop = true;
+	};
+	size_t r = 0;
+	for (size_t k = 0; k < nst && k < sl.size() && !zg_is_error(r); k++) r = upload(k);
+	if (!zg_is_error(r)) {
+		struct Joiner {
+			std::vector<std::thread> th;
+			~Joiner() {
+				for (auto& t : th)
+					if (t.joinable()) t.join();
+			}
+		} joiner;
+		for (size_t w = 1; w < nw; w++) joiner.th.emplace_back([&work, w] {
+			try {
+				work(w);
+			} catch (...) {
+			}
+		});
+		work(0);
+	}
+	size_t first_err = 0;
+	{
+		u64 best = ~0ull;
+		for (const Result& R : res) {
+			if (R.fatal && !zg_is_error(r)) r = R.fatal;
+			if (R.first_err && R.first_err_slice < best) best = R.first_err_slice, first_err = R.first_err;
 		}
 	}
 	cudaError_t e1 = cudaStreamSynchronize(d->s_in), e2 = cudaStreamSynchronize(d->s_out);

@@ -477,7 +477,8 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 		ZG_ALLOC(st.h_meta.reserve(m * 8));
 		u64* h = st.h_meta.as<u64>();
 		for (u64 i = 0; i < m; i++) h[i] = off[q.i0 + i] - q.lo;
-		ZG_CUDA(cudaStreamWaitEvent(c->s_in, st.out_done, 0));  // the stage's previous results have left
+		// (the stage's input buffers are free: the slice that used them has been packed.  Its RESULTS may still be on
+		// their way down -- that is the packing stream's wait below, not this upload's: both directions stay busy)
 		u64* dm = st.d_meta.as<u64>();
 		if (span) ZG_CUDA(cudaMemcpyAsync(st.d_blob.p, blob + q.lo, span, cudaMemcpyHostToDevice, c->s_in));
 		ZG_CUDA(cudaMemcpyAsync(dm, h, m * 8, cudaMemcpyHostToDevice, c->s_in));
@@ -510,7 +511,8 @@ static size_t pack_host(zg_cctx* c, ZgArchive& A, const uint8_t* blob, const uin
 		u64* dm = st.d_meta.as<u64>();
 		u64 cap = zg_min<u64>(st.d_frames.cap, frames_cap - written);
 		u64 bytes = 0;
-		if (cudaStreamWaitEvent(s, st.in_done, 0) != cudaSuccess) {
+		// the slice's input has arrived, and the stage's previous results have left
+		if (cudaStreamWaitEvent(s, st.in_done, 0) != cudaSuccess || cudaStreamWaitEvent(s, st.out_done, 0) != cudaSuccess) {
 			r = ZG_ERR(ZG_error_device);
 			break;
 		}
