@@ -30,8 +30,13 @@
 #endif
 // The match finder is bound by the latency of its own dependent steps, so what counts is how many warps an SM holds,
 // and that is set by the hash table in shared memory.  The largest table is 63/64 of 2^12 entries: one CTA more per SM
-// (28 warps instead of 24) for 1.6 % fewer entries.
-#define ZE_TAB_ENTRIES 4032u
+// (28 warps instead of 24) for 1.6 % fewer entries.  Smaller still (-DZE_TAB_FOLD=55u -DZE_MIN_CTAS=8: 32 warps; 48u / 9:
+// 36 warps) the kernel keeps getting faster -- 23.7 -> 22.2 -> 21.2 ms per 2 GiB, pack 51.2 -> 53.3 -> 54.8 GB/s -- but
+// the ratio pays (C2 level 3: 2.537 -> 2.523 -> 2.512); 63 kept.
+#ifndef ZE_TAB_FOLD
+#define ZE_TAB_FOLD 63u   // table entries / 64
+#endif
+#define ZE_TAB_ENTRIES (ZE_TAB_FOLD * 64u)
 #ifndef ZE_ENT_CTAS
 #define ZE_ENT_CTAS 6   // K3a/K3b: CTAs per SM
 #endif
@@ -870,14 +875,14 @@ ZG_DEV_NOINLINE u32 ze_seq_table(ZeWarp* W, const ZeCT& predef, u32 t, const u32
 // hlog bits of multiplicative hash; a full-size table (hlog = ZE_HLOG_MAX) is folded onto its ZE_TAB_ENTRIES slots
 ZG_DEV u32 ze_hash4(u32 v, u32 hlog) {
 	u32 h = (v * 2654435761u) >> (32 - hlog);
-	return hlog == ZE_HLOG_MAX ? (h * 63u) >> 6 : h;
+	return hlog == ZE_HLOG_MAX ? (h * ZE_TAB_FOLD) >> 6 : h;
 }
 
 // set index of a WAYS-way table: (hlog - LW) bits, folded like ze_hash4 when the table is full size
 template <u32 LW>
 ZG_DEV u32 ze_hash_set(u32 v, u32 hlog) {
 	u32 h = (v * 2654435761u) >> (32 - (hlog - LW));
-	return hlog == ZE_HLOG_MAX ? (h * 63u) >> 6 : h;
+	return hlog == ZE_HLOG_MAX ? (h * ZE_TAB_FOLD) >> 6 : h;
 }
 
 // what the level and the --zstd parameters (pack.rs:140-195) resolve to, see ze_resolve_params
