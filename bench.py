@@ -565,6 +565,13 @@ def main():
         extras_on = [x for x in args.extras.split(",") if x]
 
     # -------------------------------------------------------------------------------------------
+    # the helper libraries of the host-side legs (workload generator, C oracle) are built here, once per process, not by
+    # every forked worker at the same time (the builds themselves are atomic: temp file + rename)
+    from oracle import ref_path as _rp
+    from zarc_b200 import build as _build
+
+    _build.build_corpus_host()
+    _rp.build_c_oracle()
     if args.impl == "reference":
         if rank != 0:
             return
@@ -594,7 +601,7 @@ def main():
         return
 
     # -------------------------------------------------------------------------------------------
-    # host-side work first (fork before CUDA is initialised): CPU baseline (rank 0, N=1) and the C5 producer
+    # host-side work first (fork before CUDA is initialised): CPU baseline (rank 0, N=1) and the C5 producer.
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "c2":
         sample = int(args.cpu_sample_mb_per_core * 1e6 * cores)

@@ -263,7 +263,13 @@ def build_c_oracle(force: bool = False) -> str:
     so = os.path.join(_HERE, "libzarc_oracle.so")
     src = os.path.join(_HERE, "zarc_oracle.c")
     if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src])
+        tmp = f"{so}.{os.getpid()}.tmp"  # (atomic: several processes may load or rebuild it at once)
+        try:
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", tmp, src])
+            os.replace(tmp, so)
+        finally:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
     return so
 
 

@@ -37,6 +37,18 @@ def _stale(target: str, extra: list[str] = ()) -> bool:
     return os.path.getmtime(target) < m
 
 
+def _into(target: str, make) -> None:
+    """Run make(tmp) and move tmp over target: a process that loads the target while another one rebuilds it (the forked
+    workers of bench.py's CPU arm, pytest-xdist) sees the old file or the new one, never half of one."""
+    tmp = f"{target}.{os.getpid()}.tmp"
+    try:
+        make(tmp)
+        os.replace(tmp, target)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
+
+
 def build_product(force: bool = False, verbose: bool = False) -> str:
     """nvcc -> zarc_b200/libzarcgpu.so.  Cross-compiles without a GPU."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -63,7 +75,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", PRODUCT_SO, *objs, "-lcudart"])
+    _into(PRODUCT_SO, lambda tmp: subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs, "-lcudart"]))
     return PRODUCT_SO
 
 
@@ -103,8 +115,8 @@ def build_host(force: bool = False) -> str:
     deps = glob.glob(os.path.join(HOST_DIR, "*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
     if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(os.path.getmtime(f) for f in deps):
         return HOST_BIN
-    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Wno-missing-field-initializers",
-                           *srcs, "-o", HOST_BIN, "-ldl"])
+    _into(HOST_BIN, lambda tmp: subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-Wall", "-Wextra", "-Wno-unused-parameter",
+                                                       "-Wno-missing-field-initializers", *srcs, "-o", tmp, "-ldl"]))
     return HOST_BIN
 
 
@@ -118,8 +130,8 @@ def build_corpus_host(force: bool = False) -> str:
     deps = [src, os.path.join(CSRC, "corpus.cuh"), os.path.join(CSRC, "simt.h")]
     if not force and os.path.exists(CORPUS_SO) and os.path.getmtime(CORPUS_SO) >= max(os.path.getmtime(f) for f in deps):
         return CORPUS_SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DZG_EMU", "-I", EMU_DIR, "-I", CSRC, "-Wno-unused-function",
-                           src, "-o", CORPUS_SO])
+    _into(CORPUS_SO, lambda tmp: subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DZG_EMU", "-I", EMU_DIR, "-I", CSRC,
+                                                        "-Wno-unused-function", src, "-o", tmp]))
     return CORPUS_SO
 
 
