@@ -842,6 +842,7 @@ def main():
         nb_e = np.zeros(1, dtype=np.uint64)
         cctx, dctx = rt.cctx, rt.dctx
         e2e_t = [0.0, 0.0]
+        e2e_steps = []
 
         def e2e_step():
             t0 = time.perf_counter()
@@ -852,8 +853,10 @@ def main():
             rel = h_foff - 12
             lib.check(lib.zg_unpack_batch(dctx, h_frames.data_ptr(), int(nb_e[0]), ne, rel.data_ptr(), h_flen.data_ptr(), h_len.data_ptr(),
                                           h_dig.data_ptr(), h_out.data_ptr(), Be, None, h_ok.data_ptr(), h_status.data_ptr()))
+            t2 = time.perf_counter()
             e2e_t[0] += t1 - t0  # both calls return with their results on the host (blocking API)
-            e2e_t[1] += time.perf_counter() - t1
+            e2e_t[1] += t2 - t1
+            e2e_steps.append([round((t1 - t0) * 1e3, 1), round((t2 - t1) * 1e3, 1)])
 
         for _ in range(2):
             e2e_step()
@@ -862,6 +865,7 @@ def main():
         s0, s1 = cx.ev(), cx.ev()
         ksteps = max(2, min(args.steps, 5))
         e2e_t[0] = e2e_t[1] = 0.0
+        e2e_steps.clear()
         s0.record()
         for _ in range(ksteps):
             e2e_step()
@@ -872,10 +876,60 @@ def main():
         e2e = {"value": cx.rank_sum(float(Be)) / (e_ms * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(span + 16 * ne + Ce + 56 * ne), "d2h_bytes_per_step": int(Ce + 49 * ne + Be + 5 * ne),
                "ms_per_step": e_ms, "pack_ms": e2e_t[0] / ksteps * 1e3, "unpack_ms": e2e_t[1] / ksteps * 1e3,
-               "workload_gb_per_gpu": Be / 1e9, "whole_shard": bool(ne == n),
+               "rank0_step_ms_pack_unpack": list(e2e_steps), "workload_gb_per_gpu": Be / 1e9, "whole_shard": bool(ne == n),
                "api": "zg_pack_batch + zg_unpack_batch (host buffers, pinned), digests verified"}
+        # the host link of THIS box, measured on the same pinned buffers right after the timed steps (tools/linkbench.py's
+        # method: 1 GiB per direction, all ranks released together, slowest rank's device time; boxes differ by 10-30 %)
+        live = None
+        try:
+            nb = min(1 << 30, span, Be)
+            d_a = torch.empty(nb, dtype=torch.uint8, device=dev)
+            d_b = torch.empty(nb, dtype=torch.uint8, device=dev)
+            s2 = torch.cuda.Stream()
+
+            def _h2d():
+                d_a.copy_(h_blob[:nb], non_blocking=True)
+
+            def _d2h():
+                h_out[:nb].copy_(d_b, non_blocking=True)
+
+            def _both():
+                s2.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s2):
+                    h_out[:nb].copy_(d_b, non_blocking=True)
+                d_a.copy_(h_blob[:nb], non_blocking=True)
+                torch.cuda.current_stream().wait_stream(s2)
+
+            live = {}
+            for name, fn in (("h2d_gbs", _h2d), ("d2h_gbs", _d2h), ("duplex_each_way_gbs", _both)):
+                fn()
+                best = 1e30
+                for _ in range(3):
+                    cx.sync_all()
+                    a, b = cx.ev(), cx.ev()
+                    a.record()
+                    for _ in range(2):
+                        fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    best = min(best, cx.rank_max(a.elapsed_time(b)))
+                live[name] = world * 2 * nb / best / 1e6
+            del d_a, d_b
+        except Exception as e:
+            live = {"error": f"{type(e).__name__}: {e}"}
         lp = os.path.join(ROOT, "profiles", "host_link.json")
-        if os.path.exists(lp):
+        if live and "duplex_each_way_gbs" in live:
+            # one step moves max(h2d, d2h) bytes per rank each way; the link runs both ways at once
+            ceil_ms = max(e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]) * world / (live["duplex_each_way_gbs"] * 1e6)
+            # pack is an upload with a smaller download beside it, unpack the reverse: the two calls run one after the
+            # other, so the step cannot be shorter than each call's larger direction at that direction's own rate
+            serial_ms = (span * world / (live["h2d_gbs"] * 1e6)) + (Be * world / (live["d2h_gbs"] * 1e6))
+            e2e["link_ceiling"] = {"aggregate_duplex_gbs_each_way": live["duplex_each_way_gbs"], "h2d_gbs": live["h2d_gbs"], "d2h_gbs": live["d2h_gbs"],
+                                   "ms_per_step_at_ceiling": ceil_ms, "frac_of_ceiling": ceil_ms / e_ms,
+                                   "ms_per_step_pack_upload_plus_unpack_download": serial_ms, "frac_of_serial_bound": serial_ms / e_ms,
+                                   "source": "measured in this run on the e2e's own pinned buffers (1 GiB per direction, all ranks at once, "
+                                             "slowest rank's CUDA-event time), right after the timed steps"}
+        elif os.path.exists(lp):
             try:
                 L = json.load(open(lp))
                 key = str(world)
