@@ -50,6 +50,10 @@ def main():
     args = ap.parse_args()
     lib = product_lib()
     res = {}
+    import ctypes as C
+
+    if os.environ.get("ZG_DECODE_SHARE"):  # tuning aid: first batches = 4 / q of a warp's fair share of the frames
+        lib.dll.zg_internal_set_decode_share(C.c_uint32(int(os.environ["ZG_DECODE_SHARE"])))
     if os.environ.get("ZG_DECODE_BATCHING"):  # tuning aid: "cap_div,min_batch_bytes,floor_bytes" (zstd_decode.cu: the hand-out)
         import ctypes as C
 
@@ -230,7 +234,15 @@ def main():
             lib.check(lib.zg_unpack_batch_dev(dctx, d_frames.data_ptr(), int(nbytes[0]), n, d_foff0.data_ptr(), d_flen.data_ptr(), ln.data_ptr(),
                                               d_dig.data_ptr(), d_out.data_ptr(), c.blob_bytes, off.data_ptr(), d_ok.data_ptr(), d_status.data_ptr()))
 
+        lib.zg_profile_enable(1)
         best, med = timeit(run_unpack, iters=3, warmup=1)
+        lib.zg_profile_enable(0)
+        for k, name in ((0, "blake3_verify"), (2, "decode")):
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            lib.zg_profile_read(k, C.byref(ms), C.byref(cnt))
+            if cnt.value:
+                res[f"ms_{name}"] = round(ms.value / cnt.value, 3)
+        res["unpack_ms"] = round(best, 3)
         res[f"unpack_own_c2_gbs"] = c.total_bytes / best / 1e6
         res["roundtrip_ok"] = bool(int(d_ok.sum()) == n and torch.equal(d_out[: c.blob_bytes], blob[: c.blob_bytes]))
         lib.zg_cctx_free(cctx)

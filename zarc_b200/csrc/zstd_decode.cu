@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(ZD_WARPS * 32, ZD_MIN_CTAS)
 k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64* __restrict__ off, const u64* __restrict__ len,
                      const u64* __restrict__ ulen, const u64* __restrict__ out_off, u64 nframes, u8* out, u64 out_cap,
                      const u32* __restrict__ perm, const u32* __restrict__ list, u64* seq_arenas, u8* litbufs, u32* tabs, u8* hufsaves, u32* queue,
-                     u32* status, u64* produced, u32* cksums, u32 cap_div, u32 min_batch, u32 floor_bytes) {
+                     u32* status, u64* produced, u32* cksums, u32 cap_div, u32 min_batch, u32 floor_bytes, u32 share_q) {
 	ZG_DYN_SMEM(ZdWarp, sm);
 	u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	ZdWarp* W = &sm[warp];
@@ -105,7 +105,7 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 				flen = len[list ? list[t0] : t0];
 			}
 			u64 left = nframes > prev_base ? nframes - prev_base : 1;
-			u64 share = left / (2ull * gridDim.x * ZD_WARPS);
+			u64 share = 4 * left / ((u64)share_q * gridDim.x * ZD_WARPS);  // share_q quarters of ... (8: half a fair share)
 			// a quarter of a warp's fair share of the input, but at least min_batch bytes
 			u64 cap = zg_max<u64>(min_batch, archive_len / ((u64)cap_div * gridDim.x * ZD_WARPS));
 			u64 fit = cap / (flen ? flen : 1);
@@ -210,7 +210,8 @@ k_zstd_decode_frames(const u8* __restrict__ archive, u64 archive_len, const u64*
 
 // hand-out tuning (see the kernel): a batch holds at most 1/cap_div of a warp's fair share of the input but at least
 // min_batch bytes; frames so small that 32 of them stay below floor_bytes always go out as full rows
-static u32 g_zd_tune[3] = {4, ZD_BATCH_BYTES, 32u << 10};
+static u32 g_zd_tune[4] = {4, ZD_BATCH_BYTES, 32u << 10, 8};
+extern "C" void zg_internal_set_decode_share(u32 q) { g_zd_tune[3] = q ? q : 8; }
 extern "C" void zg_internal_set_decode_batching(u32 cap_div, u32 min_batch, u32 floor_bytes) {
 	g_zd_tune[0] = cap_div ? cap_div : 4;
 	g_zd_tune[1] = min_batch ? min_batch : ZD_BATCH_BYTES;
@@ -251,7 +252,7 @@ size_t zd_fused_launch(cudaStream_t s, ZgZdWork& w, const u8* archive, u64 archi
 	zg_prof_begin(ZG_K_DECODE, s);
 	ZG_LAUNCH(k_zstd_decode_frames, grid, ZD_WARPS * 32, smem, s, archive, archive_len, off, len, ulen, out_off, count, out, out_cap,
 	          perm, list, w.seqs.as<u64>(), w.lit.as<u8>(), w.tabs.as<u32>(), w.hufsave.as<u8>(), w.queue.as<u32>(), status, produced, cksums,
-	          g_zd_tune[0], g_zd_tune[1], g_zd_tune[2]);
+	          g_zd_tune[0], g_zd_tune[1], g_zd_tune[2], g_zd_tune[3]);
 	zg_prof_end(ZG_K_DECODE, s);
 	ZG_COUNT_LAUNCH();
 	return cudaGetLastError() == cudaSuccess ? 0 : ZG_ERR(ZG_error_device);
