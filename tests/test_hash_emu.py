@@ -6,7 +6,7 @@ from oracle import ref_path
 from tests.helpers import blake3_batch, xxh64_batch
 
 SIZES = [0, 1, 3, 63, 64, 65, 127, 128, 1023, 1024, 1025, 2047, 2048, 2049, 3 * 1024, 5000, 8191, 8192, 8193, 9247, 31 * 1024, 32 * 1024,
-         32 * 1024 + 1, 33 * 1024, 64 * 1024, 65 * 1024 + 7, 100_000, 128 * 1024 + 5]
+         32 * 1024 + 1, 33 * 1024, 64 * 1024, 65 * 1024 + 7, 100_000, 128 * 1024 - 1, 128 * 1024, 128 * 1024 + 5, 200_000, 300 * 1024 + 33]
 
 
 def _data(n, seed=0):

@@ -124,7 +124,12 @@ ZG_DEV u64 xx_hash(const u8* p, u64 n, u64 seed) {
 // time, coalesced and one chunk ahead, into shared memory, and lanes 0..3 run one accumulator each
 // from there: the chain's arithmetic latency is all that is left (2 GB/s per input; many inputs run
 // side by side).  `sb`: XX_SB_WORDS u64 of shared memory per warp.  All lanes call; all lanes get the hash.
-#define XX_WARP_MIN 8192u
+// (threshold: below it one THREAD per input -- four accumulators interleaved, every lane of a warp busy on its own input.
+// On a source tree (1-64 KiB files) thresholds of 8 / 32 / 128 KiB hash at 1 723 / 1 873 / 1 985 GB/s: the warp path pays
+// for its hand-offs and its serial tail on inputs this small; it is for inputs whose own chain is the critical path)
+#ifndef XX_WARP_MIN
+#define XX_WARP_MIN 131072u
+#endif
 #define XX_PREFETCH_CHUNKS 16u
 // a warp's unit of work: 2 KiB (64 stripes per accumulator chain between two warp-wide hand-offs; with 1 KiB the
 // hand-off -- products, stores, barrier, the first loads of the chain -- was 22 % of a chunk's time)
