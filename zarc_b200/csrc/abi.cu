@@ -901,7 +901,8 @@ size_t zg_decompress_stream(zg_dctx* d, zg_out_buffer* output, zg_in_buffer* inp
 #include <utility>
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof[ZG_K_COUNT];
-static cudaEvent_t g_prof_open[ZG_K_COUNT];
+static std::mutex g_prof_mu;                             // (zg_unpack_batch decodes on two host threads)
+static thread_local cudaEvent_t g_prof_open[ZG_K_COUNT];  // begin / end pairs belong to one thread
 void zg_prof_begin(int k, cudaStream_t s) {
 	if (!g_prof_on) return;
 	cudaEvent_t a;
@@ -914,6 +915,7 @@ void zg_prof_end(int k, cudaStream_t s) {
 	cudaEvent_t b;
 	cudaEventCreate(&b);
 	cudaEventRecord(b, s);
+	std::lock_guard<std::mutex> lk(g_prof_mu);
 	g_prof[k].push_back({g_prof_open[k], b});
 }
 extern "C" {
@@ -921,6 +923,7 @@ void zg_profile_enable(int on) { g_prof_on = on != 0; }
 // total device milliseconds and launch count of kernel class k since the last read
 size_t zg_profile_read(int k, double* ms, uint64_t* launches) {
 	if (k < 0 || k >= ZG_K_COUNT) return ZG_ERR(ZG_error_parameter_outOfBound);
+	std::lock_guard<std::mutex> lk(g_prof_mu);
 	double t = 0;
 	for (auto& pr : g_prof[k]) {
 		cudaEventSynchronize(pr.second);
