@@ -670,10 +670,12 @@ static size_t unpack_batch_impl(zg_dctx* d, const uint8_t* archive, uint64_t arc
 					if (t.joinable()) t.join();
 			}
 		} joiner;
-		for (size_t w = 1; w < nw; w++) joiner.th.emplace_back([&work, w] {
+		for (size_t w = 1; w < nw; w++) joiner.th.emplace_back([&work, &res, &stop, w] {
 			try {
 				work(w);
-			} catch (...) {
+			} catch (...) {  // (nothing may leave a thread; an allocation failure is all that can be thrown here)
+				res[w].fatal = ZG_ERR(ZG_error_memory_allocation);
+				stop = true;
 			}
 		});
 		work(0);
