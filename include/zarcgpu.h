@@ -158,6 +158,10 @@ size_t zg_pack_batch_dev_ex(zg_cctx*, const uint8_t* blob, const uint64_t* off, 
  *   status[k]                         0 or the zstd error code for frame k
  * Returns 0 if every frame decoded, else the error of the lowest failing k (others still decode).
  * A digest mismatch is NOT an error at this boundary (frame_iterator.rs:86-88, unpack.rs:118-120).
+ * Host buffers (page-locked ones overlap the copies with the kernels): the batch goes through in slices, two of them
+ * decoding at once -- the call runs one extra host thread while it lasts and the context keeps a helper context; results
+ * do not depend on the slicing.  A context serves one call at a time (the reference owns one DCtx per frame iterator,
+ * decode/zstd_iterator.rs:29; concurrent callers use one zg_dctx each).
  */
 size_t zg_unpack_batch(zg_dctx*, const uint8_t* archive, uint64_t archive_len, uint64_t n_frames,
                        const uint64_t* off, const uint64_t* len, const uint64_t* ulen, const uint8_t* digests,
