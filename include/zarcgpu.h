@@ -170,6 +170,11 @@ size_t zg_unpack_batch_dev(zg_dctx*, const uint8_t* archive, uint64_t archive_le
                            const uint64_t* off, const uint64_t* len, const uint64_t* ulen, const uint8_t* digests,
                            uint8_t* out, uint64_t out_cap, const uint64_t* out_off, uint8_t* ok, uint32_t* status);
 
+/* Device-pointer entry points (`*_dev`): the kernels read their inputs as ALIGNED 4-byte words, so the word that holds
+ * a buffer's last byte may be read whole -- up to 3 bytes past the end, inside the same aligned word, never written and
+ * never used.  On a GPU such a word cannot leave the allocation; a byte-exact checker wants 4 bytes of slack after
+ * `archive`, `blob` and `out`.  The host-buffer entry points stage through padded device buffers of their own. */
+
 /* ---- building blocks exposed for tests / roofline measurement (device pointers) ------------- */
 size_t zg_blake3_batch_dev(void* cuda_stream, const uint8_t* blob, const uint64_t* off, const uint64_t* len,
                            uint64_t n, uint8_t* digests);

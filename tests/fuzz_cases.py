@@ -310,3 +310,63 @@ def container_directories(lib_path, first, count, log=None):
         if log and seed % 25 == 0:
             log(seed, accepted)
     return accepted
+
+
+def hostile_metadata(lib, first, count, log=None):
+    """zg_unpack_batch_dev / zg_unpack_batch over batches in which some entries carry wild offsets, lengths, sizes or
+    output offsets (beyond the archive, beyond the output, 2^63, 2^64 - 1): no crash, every untouched entry still
+    decodes (status 0), every wild one is reported in its own status entry.  (On the CPU build "device" pointers are
+    host pointers.  The buffers carry 8 bytes of slack: the kernels read aligned 4-byte words, so the word that holds a
+    buffer's last byte may be read whole -- never written; see include/zarcgpu.h.)"""
+    U = lambda v: np.array([int(x) & (2**64 - 1) for x in v], dtype=object).astype(np.uint64)  # noqa: E731
+    for seed in range(first, first + count):
+        rng = np.random.default_rng(seed)
+        pick = lambda v: int(v[int(rng.integers(0, len(v)))])  # noqa: E731
+        datas = [text(int(rng.integers(0, 20000)), seed + i) if rng.integers(0, 2) else rand(int(rng.integers(0, 5000)), seed + i)
+                 for i in range(int(rng.integers(1, 12)))]
+        frames = [ref_path.ref_compress(d, level=int(rng.choice([1, 3]))) for d in datas]
+        archive = bytearray(b"\xaa" * 7)
+        off, ln = [], []
+        for f in frames:
+            off.append(len(archive))
+            ln.append(len(f))
+            archive += f
+        n = len(frames)
+        ul = [len(d) for d in datas]
+        oo = [int(x) for x in np.cumsum([0] + ul[:-1])]
+        total = sum(ul)
+        wild = [False] * n
+        for k in range(n):
+            r = int(rng.integers(0, 8))
+            if r == 0:
+                off[k] = pick([len(archive) + 5, 2**63, 2**64 - 1, len(archive) - 1])
+            elif r == 1:
+                ln[k] = pick([0, 1, len(archive) * 2, 2**64 - 1, max(0, ln[k] - 1)])
+            elif r == 2:
+                ul[k] = pick([ul[k] + 1, max(0, ul[k] - 1) if ul[k] else 5, 2**40, 2**64 - 1])
+            elif r == 3:
+                oo[k] = pick([total + 1, 2**63, 2**64 - 1])
+            wild[k] = r <= 3
+        arch = np.frombuffer(bytes(archive) + bytes(8), dtype=np.uint8).copy()
+        a_off, a_len, a_ul, a_oo = U(off), U(ln), U(ul), U(oo)
+        out = np.zeros(max(total, 1) + 8, dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8)
+        st = np.zeros(n, dtype=np.uint32)
+        dig = np.frombuffer(b"".join(ref_path.c_blake3(d) for d in datas), dtype=np.uint8).copy()
+        d = lib.zg_dctx_create()
+        rc = lib.zg_unpack_batch_dev(d, arch.ctypes.data, len(archive), n, a_off.ctypes.data, a_len.ctypes.data, a_ul.ctypes.data,
+                                     dig.ctypes.data, out.ctypes.data, total, a_oo.ctypes.data, ok.ctypes.data, st.ctypes.data)
+        assert (rc == 0) == (not any(wild)) or not any(st), (seed, rc)
+        for k in range(n):
+            if wild[k]:
+                assert st[k] != 0 and ok[k] == 0, (seed, k, "a wild entry went through")
+            else:
+                assert st[k] == 0 and ok[k] == 1, (seed, k, int(st[k]))
+                assert bytes(out[oo[k] : oo[k] + ul[k]]) == datas[k], (seed, k)
+        # the host-buffer variant (dense output) on the same metadata: an error code or per-frame statuses, no crash
+        lib.zg_unpack_batch(d, arch.ctypes.data, len(archive), n, a_off.ctypes.data, a_len.ctypes.data, a_ul.ctypes.data, dig.ctypes.data,
+                            out.ctypes.data, total, None, ok.ctypes.data, st.ctypes.data)
+        lib.zg_dctx_free(d)
+        if log and seed % 50 == 0:
+            log(seed, seed - first + 1)
+    return count

@@ -28,3 +28,7 @@ def test_streaming_api(emu):
 
 def test_container_directories():
     assert fz.container_directories(build.build_emu(), 300, 60) >= 1
+
+
+def test_hostile_metadata(emu):
+    fz.hostile_metadata(emu, 40, 60)
