@@ -370,3 +370,35 @@ def hostile_metadata(lib, first, count, log=None):
         if log and seed % 50 == 0:
             log(seed, seed - first + 1)
     return count
+
+
+def compress_capacity(lib, first, count, log=None):
+    """zg_compress2 into destinations of every awkward capacity (0, 1, around the frame header, random, n, the
+    reference's n + max(1024, n / 10) of lowlevel_frames.rs:21): either dstSize_tooSmall or a frame of at most `cap`
+    bytes that libzstd restores; the destination is an exact-size buffer (an overrun shows under AddressSanitizer)."""
+    c = lib.zg_cctx_create()
+    lib.check(lib.zg_cctx_init(c, 0))
+    made = refused = 0
+    for seed in range(first, first + count):
+        rng = np.random.default_rng(seed)
+        data = glued_input(rng, float(rng.choice([0.05, 0.3, 1.0])))
+        n = len(data)
+        lib.check(lib.zg_cctx_set_parameter(c, 201, int(rng.integers(0, 2))))
+        lib.check(lib.zg_cctx_set_parameter(c, 100, int(rng.choice([1, 3, 9]))))
+        bound = n + max(1024, n // 10)
+        src = np.frombuffer(data + bytes(8), dtype=np.uint8).copy()
+        for cap in sorted({0, 1, 12, 13, 14, int(rng.integers(0, bound + 1)), int(rng.integers(0, bound + 1)), n // 3, n, n + 3, n + 16, bound}):
+            dst = np.full(max(cap, 1), 0xEE, dtype=np.uint8)
+            r = lib.zg_compress2(c, dst.ctypes.data, cap, src.ctypes.data, n)
+            if lib.zg_is_error(r):
+                assert lib.zg_get_error_code(r) == 70, (seed, cap, lib.zg_get_error_code(r))
+                refused += 1
+            else:
+                assert r <= cap and ref_path.ref_decompress(bytes(dst[:r]), n) == data, (seed, cap)
+                made += 1
+        full = np.zeros(bound, dtype=np.uint8)
+        assert not lib.zg_is_error(lib.zg_compress2(c, full.ctypes.data, bound, src.ctypes.data, n)), (seed, "the reference's capacity must do")
+        if log and seed % 20 == 0:
+            log(seed, made + refused)
+    lib.zg_cctx_free(c)
+    return made, refused

@@ -32,3 +32,8 @@ def test_container_directories():
 
 def test_hostile_metadata(emu):
     fz.hostile_metadata(emu, 40, 60)
+
+
+def test_compress_capacity(emu):
+    made, refused = fz.compress_capacity(emu, 7, 12)
+    assert made > 20 and refused > 20
